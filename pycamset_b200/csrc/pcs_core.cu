@@ -1,0 +1,1003 @@
+// pcs_core.cu -- problem build, parameter handling, residual / Jacobian / normal-equation kernels and
+// their C-ABI entry points (see include/pcs_b200.h for the reference interfaces each one replaces).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "pcs_internal.cuh"
+#include "pcs_math.cuh"
+
+namespace pcs {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(T** ptr, int64_t count)
+{
+    *ptr = nullptr;
+    if (count <= 0) count = 1;
+    PCS_CUDA(cudaMalloc((void**)ptr, (size_t)count * sizeof(T)));
+    return PCS_OK;
+}
+
+template <typename T>
+static void dev_free(T*& ptr)
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+}
+
+int ensure_pinned(pcs_problem* p, int64_t doubles)
+{
+    if (p->h_pin_doubles >= doubles) return PCS_OK;
+    if (p->h_pin) cudaFreeHost(p->h_pin);
+    p->h_pin = nullptr;
+    p->h_pin_doubles = 0;
+    PCS_CUDA(cudaMallocHost((void**)&p->h_pin, (size_t)doubles * sizeof(double)));
+    p->h_pin_doubles = doubles;
+    return PCS_OK;
+}
+
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------------
+// parameter kernels
+// ------------------------------------------------------------------------------------------------
+// x (free vector) -> parameter string; replaces fill_flat x3 (compiled_helpers.py:155-177)
+__global__ void k_scatter_x(int64_t n_free, const int32_t* __restrict__ free_idx, const double* __restrict__ x,
+                            double* __restrict__ params)
+{
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < n_free) params[free_idx[j]] = x[j];
+}
+
+// Per-camera / per-pose tables: rotation matrices and their derivatives are computed ONCE per parameter
+// update instead of once per observation (the reference calls Rodrigues inside the per-observation loop,
+// function_block_implementations.py:150-182).
+__global__ void k_prepare_tables(int C, int M, const double* __restrict__ params, double* __restrict__ camtab,
+                                 double* __restrict__ posetab)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < C) {
+        const double* q = params + 9 * (int64_t)t;
+        const double* e = params + 9 * (int64_t)C + 6 * (int64_t)t;
+        double* o = camtab + (int64_t)t * CAM_STRIDE;
+        for (int k = 0; k < 9; ++k) o[CAM_Q + k] = q[k];
+        double r[3] = {e[0], e[1], e[2]}, R[9], dR[27];
+        rodrigues(r, R);
+        rodrigues_jac(r, dR);
+        for (int k = 0; k < 9; ++k) o[CAM_R + k] = R[k];
+        for (int k = 0; k < 3; ++k) o[CAM_T + k] = e[3 + k];
+        for (int k = 0; k < 27; ++k) o[CAM_DR + k] = dR[k];
+    } else if (t < C + M) {
+        int m = t - C;
+        const double* e = params + 15 * (int64_t)C + 6 * (int64_t)m;
+        double* o = posetab + (int64_t)m * POSE_STRIDE;
+        double r[3] = {e[0], e[1], e[2]}, R[9], dR[27];
+        rodrigues(r, R);
+        rodrigues_jac(r, dR);
+        for (int k = 0; k < 9; ++k) o[POSE_R + k] = R[k];
+        for (int k = 0; k < 3; ++k) o[POSE_T + k] = e[3 + k];
+        for (int k = 0; k < 27; ++k) o[POSE_DR + k] = dR[k];
+        o[39] = 0.0;
+    }
+}
+
+int launch_scatter_x(pcs_problem* p, const double* x_dev)
+{
+    if (p->n_free > 0) {
+        k_scatter_x<<<grid_for(p->n_free, 256), 256, 0, p->stream>>>(p->n_free, p->free_idx, x_dev, p->params);
+        PCS_CUDA(cudaGetLastError());
+    }
+    return PCS_OK;
+}
+
+int launch_prepare(pcs_problem* p)
+{
+    k_prepare_tables<<<grid_for(p->C + p->M, 128), 128, 0, p->stream>>>(p->C, p->M, p->params, p->camtab, p->posetab);
+    PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+static inline const double* points_ptr(const pcs_problem* p)
+{
+    return p->chain == PCS_CHAIN_TEMPLATE ? p->tmpl : p->params + 15 * (int64_t)p->C + 6 * (int64_t)p->M;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_res: residual, one thread per observation, dd row order.  44 algorithmic bytes / observation.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_residual(int64_t N, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose,
+           const int32_t* __restrict__ key, const double2* __restrict__ uv, const double* __restrict__ camtab,
+           const double* __restrict__ posetab, const double* __restrict__ pts, double2* __restrict__ r_out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int c = cam[i], m = pose[i], k = key[i];
+    const double2 o = uv[i];
+    const double* pt = pts + 3 * (int64_t)k;
+    const double Xt[3] = {pt[0], pt[1], pt[2]};
+    double res[2];
+    eval_residual(camtab + (int64_t)c * CAM_STRIDE, posetab + (int64_t)m * POSE_STRIDE, Xt, o.x, o.y, res);
+    r_out[i] = make_double2(res[0], res[1]);
+}
+
+int launch_residual(pcs_problem* p, double* r_dev)
+{
+    if (p->N == 0) return PCS_OK;
+    k_residual<<<grid_for(p->N, 256), 256, 0, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv,
+                                                          p->camtab, p->posetab, points_ptr(p), (double2*)r_dev);
+    PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+// cost-only evaluation (LM step acceptance): residual in registers, block reduction, one atomic per CTA
+__global__ void __launch_bounds__(256)
+k_cost(int64_t N, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose, const int32_t* __restrict__ key,
+       const double2* __restrict__ uv, const double* __restrict__ camtab, const double* __restrict__ posetab,
+       const double* __restrict__ pts, double* __restrict__ cost)
+{
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = cam[i], m = pose[i], k = key[i];
+        const double2 o = uv[i];
+        const double* pt = pts + 3 * (int64_t)k;
+        const double Xt[3] = {pt[0], pt[1], pt[2]};
+        double res[2];
+        eval_residual(camtab + (int64_t)c * CAM_STRIDE, posetab + (int64_t)m * POSE_STRIDE, Xt, o.x, o.y, res);
+        acc = fma(res[0], res[0], fma(res[1], res[1], acc));
+    }
+    typedef cub::BlockReduce<double, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    double s = BR(tmp).Sum(acc);
+    if (threadIdx.x == 0) atomicAdd(cost, s);
+}
+
+int launch_cost_only(pcs_problem* p, double* cost_dev)
+{
+    PCS_CUDA(cudaMemsetAsync(cost_dev, 0, sizeof(double), p->stream));
+    if (p->N == 0) return PCS_OK;
+    int grid = std::min<int64_t>(grid_for(p->N, 256), (int64_t)p->sm_count * 8);
+    k_cost<<<grid, 256, 0, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab, p->posetab,
+                                        points_ptr(p), cost_dev);
+    PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_jac: explicit CSR values in the reference's order.  One thread per observation evaluates the 2 x P
+// row pair in registers; a warp's rows are contiguous in the CSR value array, so they are compacted
+// (fixed columns dropped) into shared memory and written back with coalesced stores.
+// 28 B in + 16 P B out per observation.
+// ------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(128)
+k_jacobian(int64_t N, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose, const int32_t* __restrict__ key,
+           const double2* __restrict__ uv, const double* __restrict__ camtab, const double* __restrict__ posetab,
+           const double* __restrict__ pts, const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask,
+           const uint8_t* __restrict__ key_mask, const int64_t* __restrict__ row_prefix, double* __restrict__ vals)
+{
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* ws = sm + warp * (64 * P);
+    const int64_t w0 = (blockIdx.x * (int64_t)(blockDim.x >> 5) + warp) * 32;
+    if (w0 >= N) return;
+    const int64_t i = w0 + lane;
+    const int64_t wend = min(N, w0 + 32);
+    const int64_t base = row_prefix[w0];
+    const int64_t total = 2 * (row_prefix[wend] - base);
+    if (i < N) {
+        const int c = cam[i], m = pose[i], k = key[i];
+        const double2 o = uv[i];
+        const double* pt = pts + 3 * (int64_t)k;
+        const double Xt[3] = {pt[0], pt[1], pt[2]};
+        const double* ct = camtab + (int64_t)c * CAM_STRIDE;
+        const double* ptab = posetab + (int64_t)m * POSE_STRIDE;
+        double res[2], Xw[3];
+        ObsJac J;
+        eval_obs(ct, ptab, Xt, o.x, o.y, res, J, Xw);
+        double ju[P], jv[P];
+        expand_rows<P>(J, ptab + POSE_R, ju, jv);
+        uint32_t mask = (uint32_t)cam_mask[c] | ((uint32_t)pose_mask[m] << 15);
+        if (P == 24) mask |= (uint32_t)key_mask[k] << 21;
+        const int n = __popc(mask);
+        int off = (int)(2 * (row_prefix[i] - base));
+        double* du = ws + off;
+        double* dv = du + n;
+        int w = 0;
+#pragma unroll
+        for (int col = 0; col < P; ++col) {
+            if (mask & (1u << col)) {
+                du[w] = ju[col];
+                dv[w] = jv[col];
+                ++w;
+            }
+        }
+    }
+    __syncwarp();
+    double* out = vals + 2 * base;
+    for (int64_t t = lane; t < total; t += 32) out[t] = ws[t];
+}
+
+// CSR structure (make_jac_CSR_columns_row_pointers, abstract_function_blocks.py:465-489)
+__global__ void k_csr_structure(int64_t N, int P, int C, int M, const int32_t* __restrict__ cam,
+                                const int32_t* __restrict__ pose, const int32_t* __restrict__ key,
+                                const int32_t* __restrict__ free_map, const int64_t* __restrict__ row_prefix,
+                                int64_t* __restrict__ col_idx, int64_t* __restrict__ row_ptr)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > N) return;
+    if (i == N) {
+        row_ptr[2 * N] = 2 * row_prefix[N];
+        return;
+    }
+    const int64_t s = row_prefix[i], n = row_prefix[i + 1] - s;
+    row_ptr[2 * i] = 2 * s;
+    row_ptr[2 * i + 1] = 2 * s + n;
+    const int64_t c = cam[i], m = pose[i], k = key[i];
+    int64_t w = 2 * s;
+    for (int col = 0; col < P; ++col) {
+        int64_t g;
+        if (col < 9) g = 9 * c + col;
+        else if (col < 15) g = 9 * (int64_t)C + 6 * c + (col - 9);
+        else if (col < 21) g = 15 * (int64_t)C + 6 * m + (col - 15);
+        else g = 15 * (int64_t)C + 6 * (int64_t)M + 3 * k + (col - 21);
+        const int32_t f = free_map[g];
+        if (f >= 0) {
+            col_idx[w] = f;
+            col_idx[w + n] = f;
+            ++w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_ne v1 (reference implementation on the device; superseded by the tiled kernel in pcs_normal.cu):
+// (camera, pose)-sorted observations; a warp stages the augmented rows J' = [J | r] of 32 observations
+// in shared memory, then every lane owns 8 of the 253 upper-triangle entries of J'^T J' and walks the
+// observations; entries are flushed with FP64 atomics when the segment / camera changes.
+// ------------------------------------------------------------------------------------------------
+constexpr int NE_COLS = 22;
+constexpr int NE_ENT = NE_COLS * (NE_COLS + 1) / 2;  // 253
+__constant__ uint8_t c_ent_a[256];
+__constant__ uint8_t c_ent_b[256];
+
+__device__ __forceinline__ void ne_flush_entry(double v, int a, int b, int c, int m, int64_t seg, double* U, double* gc,
+                                               double* cost, double* V, double* gp, double* W)
+{
+    if (v == 0.0) return;
+    if (a < 15) {
+        if (b < 15) atomicAdd(U + (int64_t)c * 225 + a * 15 + b, v);
+        else if (b < 21) atomicAdd(W + seg * 90 + a * 6 + (b - 15), v);
+        else atomicAdd(gc + (int64_t)c * 15 + a, v);
+    } else if (a < 21) {
+        if (b < 21) atomicAdd(V + (int64_t)m * 36 + (a - 15) * 6 + (b - 15), v);
+        else atomicAdd(gp + (int64_t)m * 6 + (a - 15), v);
+    } else {
+        atomicAdd(cost, v);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_normal_v1(int64_t N, int64_t obs_per_warp, const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv,
+            const int32_t* __restrict__ s_seg, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose,
+            const double* __restrict__ camtab, const double* __restrict__ posetab, const double* __restrict__ pts,
+            double* U, double* gc, double* cost, double* V, double* gp, double* W)
+{
+    constexpr int LD = 2 * NE_COLS + 1;  // 45: odd stride -> spread banks
+    __shared__ double Jsm[4][32 * LD];
+    __shared__ int segsm[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* js = Jsm[warp];
+    int* ss = segsm[warp];
+    const int64_t wg = blockIdx.x * (int64_t)(blockDim.x >> 5) + warp;
+    const int64_t begin = wg * obs_per_warp;
+    const int64_t end = min(N, begin + obs_per_warp);
+    if (begin >= N) return;
+
+    int ea[8], eb[8];
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int e = lane + 32 * j;
+        ea[j] = e < NE_ENT ? c_ent_a[e] : 0;
+        eb[j] = e < NE_ENT ? c_ent_b[e] : 0;
+        acc[j] = 0.0;
+    }
+    int64_t cur_seg = -1;
+    int cur_c = -1, cur_m = -1;
+
+    for (int64_t base = begin; base < end; base += 32) {
+        const int64_t i = base + lane;
+        int seg = -1;
+        double* row = js + lane * LD;
+        if (i < end) {
+            seg = s_seg[i];
+            const int c = seg_cam[seg], m = seg_pose[seg];
+            const int k = s_key[i];
+            const double2 o = s_uv[i];
+            const double* pt = pts + 3 * (int64_t)k;
+            const double Xt[3] = {pt[0], pt[1], pt[2]};
+            const double* ptab = posetab + (int64_t)m * POSE_STRIDE;
+            double res[2], Xw[3];
+            ObsJac J;
+            eval_obs(camtab + (int64_t)c * CAM_STRIDE, ptab, Xt, o.x, o.y, res, J, Xw);
+            double ju[21], jv[21];
+            expand_rows<21>(J, ptab, ju, jv);
+#pragma unroll
+            for (int col = 0; col < 21; ++col) {
+                row[col] = ju[col];
+                row[NE_COLS + col] = jv[col];
+            }
+            row[21] = res[0];
+            row[NE_COLS + 21] = res[1];
+        }
+        ss[lane] = seg;
+        __syncwarp();
+        const int cnt = (int)min((int64_t)32, end - base);
+        for (int o = 0; o < cnt; ++o) {
+            const int so = ss[o];
+            if (so != cur_seg) {
+                const int nc = seg_cam[so], nm = seg_pose[so];
+                if (cur_seg >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const bool cam_class = (ea[j] < 15 && (eb[j] < 15 || eb[j] == 21)) || ea[j] == 21;
+                        if (!cam_class || nc != cur_c) {
+                            if (lane + 32 * j < NE_ENT)
+                                ne_flush_entry(acc[j], ea[j], eb[j], cur_c, cur_m, cur_seg, U, gc, cost, V, gp, W);
+                            acc[j] = 0.0;
+                        }
+                    }
+                }
+                cur_seg = so; cur_c = nc; cur_m = nm;
+            }
+            const double* r = js + o * LD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                acc[j] = fma(r[ea[j]], r[eb[j]], fma(r[NE_COLS + ea[j]], r[NE_COLS + eb[j]], acc[j]));
+        }
+        __syncwarp();
+    }
+    if (cur_seg >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (lane + 32 * j < NE_ENT) ne_flush_entry(acc[j], ea[j], eb[j], cur_c, cur_m, cur_seg, U, gc, cost, V, gp, W);
+    }
+}
+
+// mirror the upper triangles of U (15x15) and V (6x6) into the lower ones
+__global__ void k_symmetrize_blocks(int64_t n_blocks, int dim, double* __restrict__ blocks)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int per = dim * dim;
+    if (t >= n_blocks * per) return;
+    const int64_t blk = t / per;
+    const int e = (int)(t % per), a = e / dim, b = e % dim;
+    if (a > b) blocks[blk * per + e] = blocks[blk * per + b * dim + a];
+}
+
+int launch_normal_blocks_v1(pcs_problem* p)
+{
+    PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)p->ne_doubles * sizeof(double), p->stream));
+    if (p->N > 0) {
+        // ~8 warps' worth of work per SM-resident warp slot; each warp walks a contiguous range
+        int64_t warps = std::max<int64_t>(1, std::min<int64_t>((p->N + 255) / 256, (int64_t)p->sm_count * 64));
+        int64_t per = ((p->N + warps - 1) / warps + 31) / 32 * 32;
+        warps = (p->N + per - 1) / per;
+        int grid = (int)((warps + 3) / 4);
+        k_normal_v1<<<grid, 128, 0, p->stream>>>(p->N, per, p->s_key, (const double2*)p->s_uv, p->s_seg, p->seg_cam,
+                                                 p->seg_pose, p->camtab, p->posetab, points_ptr(p), p->U, p->gc, p->cost,
+                                                 p->V, p->gp, p->W);
+        PCS_CUDA(cudaGetLastError());
+    }
+    k_symmetrize_blocks<<<grid_for((int64_t)p->C * 225, 256), 256, 0, p->stream>>>(p->C, 15, p->U);
+    k_symmetrize_blocks<<<grid_for((int64_t)p->M * 36, 256), 256, 0, p->stream>>>(p->M, 6, p->V);
+    PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense normal equations over the free parameters (both chains; small problems)
+// ------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(128)
+k_normal_dense(int64_t N, int C, int M, int64_t n_free, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose,
+               const int32_t* __restrict__ key, const double2* __restrict__ uv, const double* __restrict__ camtab,
+               const double* __restrict__ posetab, const double* __restrict__ pts, const int32_t* __restrict__ free_map,
+               double* JtJ, double* Jtr, double* cost)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t c = cam[i], m = pose[i], k = key[i];
+    const double2 o = uv[i];
+    const double* pt = pts + 3 * k;
+    const double Xt[3] = {pt[0], pt[1], pt[2]};
+    const double* ptab = posetab + m * POSE_STRIDE;
+    double res[2], Xw[3];
+    ObsJac J;
+    eval_obs(camtab + c * CAM_STRIDE, ptab, Xt, o.x, o.y, res, J, Xw);
+    double ju[P], jv[P];
+    expand_rows<P>(J, ptab + POSE_R, ju, jv);
+    int32_t f[P];
+#pragma unroll
+    for (int col = 0; col < P; ++col) {
+        int64_t g;
+        if (col < 9) g = 9 * c + col;
+        else if (col < 15) g = 9 * (int64_t)C + 6 * c + (col - 9);
+        else if (col < 21) g = 15 * (int64_t)C + 6 * m + (col - 15);
+        else g = 15 * (int64_t)C + 6 * (int64_t)M + 3 * k + (col - 21);
+        f[col] = free_map[g];
+    }
+    atomicAdd(cost, fma(res[0], res[0], res[1] * res[1]));
+#pragma unroll
+    for (int a = 0; a < P; ++a) {
+        if (f[a] < 0) continue;
+        atomicAdd(Jtr + f[a], fma(ju[a], res[0], jv[a] * res[1]));
+#pragma unroll
+        for (int b = a; b < P; ++b) {
+            if (f[b] < 0) continue;
+            const double v = fma(ju[a], ju[b], jv[a] * jv[b]);
+            if (v == 0.0) continue;
+            const int64_t lo = min(f[a], f[b]), hi = max(f[a], f[b]);
+            atomicAdd(JtJ + lo * n_free + hi, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// problem build kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_validate_and_count(int64_t N, int C, int M, int K, int P, const int32_t* __restrict__ cam,
+                                     const int32_t* __restrict__ pose, const int32_t* __restrict__ key,
+                                     const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask,
+                                     const uint8_t* __restrict__ key_mask, int64_t* __restrict__ counts,
+                                     uint64_t* __restrict__ sort_keys, uint32_t* __restrict__ sort_idx, int* __restrict__ bad)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > N) return;
+    if (i == N) {
+        counts[N] = 0;
+        return;
+    }
+    const int c = cam[i], m = pose[i], k = key[i];
+    if (c < 0 || c >= C || m < 0 || m >= M || k < 0 || k >= K) {
+        atomicExch(bad, 1);
+        counts[i] = 0;
+        sort_keys[i] = 0;
+        sort_idx[i] = (uint32_t)i;
+        return;
+    }
+    int n = __popc((unsigned)cam_mask[c]) + __popc((unsigned)pose_mask[m]);
+    if (P == 24) n += __popc((unsigned)key_mask[k]);
+    counts[i] = n;
+    sort_keys[i] = (uint64_t)c * (uint64_t)M + (uint64_t)m;
+    sort_idx[i] = (uint32_t)i;
+}
+
+__global__ void k_segment_flags(int64_t N, const uint64_t* __restrict__ keys, int32_t* __restrict__ flags)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < N) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// s_seg holds the inclusive scan of flags on entry (segment id + 1)
+__global__ void k_segment_fill(int64_t N, int M, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+                               const int32_t* __restrict__ key_in, const double2* __restrict__ uv_in,
+                               int32_t* __restrict__ s_seg, int32_t* __restrict__ s_key, double2* __restrict__ s_uv,
+                               int32_t* __restrict__ seg_cam, int32_t* __restrict__ seg_pose, int64_t* __restrict__ seg_start)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int32_t seg = s_seg[i] - 1;
+    s_seg[i] = seg;
+    const uint32_t src = perm[i];
+    s_key[i] = key_in[src];
+    s_uv[i] = uv_in[src];
+    if (i == 0 || keys[i] != keys[i - 1]) {
+        seg_cam[seg] = (int32_t)(keys[i] / (uint64_t)M);
+        seg_pose[seg] = (int32_t)(keys[i] % (uint64_t)M);
+        seg_start[seg] = i;
+    }
+    if (i == N - 1) seg_start[seg + 1] = N;
+}
+
+}  // namespace pcs
+
+using namespace pcs;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* pcs_last_error(void) { return g_last_error.c_str(); }
+const char* pcs_version(void) { return "pcs_b200 0.1 (sm_100a)"; }
+
+int pcs_chain_from_name(const char* name)
+{
+    if (name && std::strcmp(name, "projection_extrinsic3D_template_points") == 0) return PCS_CHAIN_TEMPLATE;
+    if (name && std::strcmp(name, "projection_extrinsic3D_rigidTform3d_free_point") == 0) return PCS_CHAIN_SELFCAL;
+    set_error(std::string("unknown function-block chain '") + (name ? name : "(null)") +
+              "': only projection_extrinsic3D_template_points and projection_extrinsic3D_rigidTform3d_free_point "
+              "have CUDA kernels; there is no CPU fallback");
+    return PCS_ERR_CHAIN;
+}
+
+int pcs_device_sm_count(int device)
+{
+    int n = 0;
+    PCS_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+    return n;
+}
+
+int pcs_problem_destroy(pcs_problem* p)
+{
+    if (!p) return PCS_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    lm_free(p);
+    dev_free(p->cam); dev_free(p->pose); dev_free(p->key); dev_free(p->uv); dev_free(p->tmpl);
+    dev_free(p->free_map); dev_free(p->free_idx); dev_free(p->cam_mask); dev_free(p->pose_mask); dev_free(p->key_mask);
+    dev_free(p->row_prefix); dev_free(p->params); dev_free(p->x); dev_free(p->camtab); dev_free(p->posetab);
+    dev_free(p->resid); dev_free(p->jvals); dev_free(p->seg_cam); dev_free(p->seg_pose); dev_free(p->seg_start);
+    dev_free(p->s_key); dev_free(p->s_seg); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense);
+    if (p->h_pin) cudaFreeHost(p->h_pin);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return PCS_OK;
+}
+
+static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
+{
+    const int64_t N = p->N;
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    if (d->stream) {
+        p->stream = (cudaStream_t)d->stream;
+    } else {
+        PCS_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        p->own_stream = true;
+    }
+    cudaStream_t st = p->stream;
+
+    // --- observation SoA -------------------------------------------------------------------
+    PCS_TRY(dev_alloc(&p->cam, N)); PCS_TRY(dev_alloc(&p->pose, N)); PCS_TRY(dev_alloc(&p->key, N));
+    PCS_TRY(dev_alloc(&p->uv, 2 * N));
+    const cudaMemcpyKind kind = d->inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (N > 0) {
+        PCS_CUDA(cudaMemcpyAsync(p->cam, d->cam, (size_t)N * 4, kind, st));
+        PCS_CUDA(cudaMemcpyAsync(p->pose, d->pose, (size_t)N * 4, kind, st));
+        PCS_CUDA(cudaMemcpyAsync(p->key, d->key, (size_t)N * 4, kind, st));
+        PCS_CUDA(cudaMemcpyAsync(p->uv, d->uv, (size_t)N * 16, kind, st));
+    }
+    if (p->chain == PCS_CHAIN_TEMPLATE) {
+        PCS_TRY(dev_alloc(&p->tmpl, 3 * (int64_t)p->K));
+        PCS_CUDA(cudaMemcpyAsync(p->tmpl, d->template_xyz, (size_t)p->K * 24, cudaMemcpyHostToDevice, st));
+    }
+
+    // --- free map, masks, free index list (host, O(L)) ---------------------------------------
+    const int64_t L = p->L;
+    std::vector<int32_t> fm(L);
+    if (d->free_map) std::memcpy(fm.data(), d->free_map, (size_t)L * 4);
+    else for (int64_t i = 0; i < L; ++i) fm[i] = (int32_t)i;
+    int64_t n_free = 0;
+    for (int64_t i = 0; i < L; ++i) if (fm[i] >= 0) ++n_free;
+    std::vector<int32_t> fidx(std::max<int64_t>(n_free, 1), -1);
+    for (int64_t i = 0; i < L; ++i) {
+        if (fm[i] < 0) continue;
+        PCS_REQUIRE(fm[i] < n_free && fidx[fm[i]] < 0, "free_map must be a bijection onto [0, n_free)");
+        fidx[fm[i]] = (int32_t)i;
+    }
+    p->n_free = n_free;
+    std::vector<uint16_t> cmask(std::max(p->C, 1));
+    std::vector<uint8_t> pmask(std::max(p->M, 1)), kmask(std::max(p->K, 1), 0);
+    for (int c = 0; c < p->C; ++c) {
+        uint16_t mk = 0;
+        for (int k = 0; k < 9; ++k) if (fm[9 * (int64_t)c + k] >= 0) mk |= (uint16_t)(1u << k);
+        for (int k = 0; k < 6; ++k) if (fm[9 * (int64_t)p->C + 6 * (int64_t)c + k] >= 0) mk |= (uint16_t)(1u << (9 + k));
+        cmask[c] = mk;
+    }
+    for (int m = 0; m < p->M; ++m) {
+        uint8_t mk = 0;
+        for (int k = 0; k < 6; ++k) if (fm[15 * (int64_t)p->C + 6 * (int64_t)m + k] >= 0) mk |= (uint8_t)(1u << k);
+        pmask[m] = mk;
+    }
+    if (p->chain == PCS_CHAIN_SELFCAL)
+        for (int k = 0; k < p->K; ++k) {
+            uint8_t mk = 0;
+            for (int j = 0; j < 3; ++j)
+                if (fm[15 * (int64_t)p->C + 6 * (int64_t)p->M + 3 * (int64_t)k + j] >= 0) mk |= (uint8_t)(1u << j);
+            kmask[k] = mk;
+        }
+    PCS_TRY(dev_alloc(&p->free_map, L)); PCS_TRY(dev_alloc(&p->free_idx, n_free));
+    PCS_TRY(dev_alloc(&p->cam_mask, p->C)); PCS_TRY(dev_alloc(&p->pose_mask, p->M)); PCS_TRY(dev_alloc(&p->key_mask, p->K));
+    PCS_CUDA(cudaMemcpyAsync(p->free_map, fm.data(), (size_t)L * 4, cudaMemcpyHostToDevice, st));
+    if (n_free) PCS_CUDA(cudaMemcpyAsync(p->free_idx, fidx.data(), (size_t)n_free * 4, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(cudaMemcpyAsync(p->cam_mask, cmask.data(), (size_t)p->C * 2, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(cudaMemcpyAsync(p->pose_mask, pmask.data(), (size_t)p->M, cudaMemcpyHostToDevice, st));
+    PCS_CUDA(cudaMemcpyAsync(p->key_mask, kmask.data(), (size_t)p->K, cudaMemcpyHostToDevice, st));
+
+    // --- dynamic state ------------------------------------------------------------------------
+    PCS_TRY(dev_alloc(&p->params, L)); PCS_TRY(dev_alloc(&p->x, n_free));
+    PCS_TRY(dev_alloc(&p->camtab, (int64_t)p->C * CAM_STRIDE)); PCS_TRY(dev_alloc(&p->posetab, (int64_t)p->M * POSE_STRIDE));
+    PCS_CUDA(cudaMemsetAsync(p->params, 0, (size_t)L * 8, st));
+
+    // --- per-observation free-column counts, sort keys ------------------------------------------
+    PCS_TRY(dev_alloc(&p->row_prefix, N + 1));
+    uint64_t *keys_a = nullptr, *keys_b = nullptr;
+    uint32_t *idx_a = nullptr, *idx_b = nullptr;
+    int* bad = nullptr;
+    int32_t* flags = nullptr;
+    void* tmp = nullptr;
+    int rc = PCS_OK;
+    auto cleanup = [&]() {
+        dev_free(keys_a); dev_free(keys_b); dev_free(idx_a); dev_free(idx_b); dev_free(bad); dev_free(flags);
+        if (tmp) cudaFree(tmp);
+    };
+#define BUILD_TRY(expr) do { rc = (expr); if (rc != PCS_OK) { cleanup(); return rc; } } while (0)
+#define BUILD_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " -> " + cudaGetErrorString(e__)); cleanup(); return PCS_ERR_CUDA; } } while (0)
+    BUILD_TRY(dev_alloc(&keys_a, N)); BUILD_TRY(dev_alloc(&keys_b, N));
+    BUILD_TRY(dev_alloc(&idx_a, N)); BUILD_TRY(dev_alloc(&idx_b, N));
+    BUILD_TRY(dev_alloc(&bad, 1)); BUILD_TRY(dev_alloc(&flags, N));
+    BUILD_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    k_validate_and_count<<<grid_for(N + 1, 256), 256, 0, st>>>(N, p->C, p->M, p->K, p->P, p->cam, p->pose, p->key,
+                                                               p->cam_mask, p->pose_mask, p->key_mask, p->row_prefix,
+                                                               keys_a, idx_a, bad);
+    BUILD_CUDA(cudaGetLastError());
+    int h_bad = 0;
+    BUILD_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BUILD_CUDA(cudaStreamSynchronize(st));
+    if (h_bad) {
+        set_error("observation table has a camera / pose / key index outside [0, n_cams) x [0, n_poses) x [0, n_keys)");
+        cleanup();
+        return PCS_ERR_INVALID;
+    }
+    size_t tmp_bytes = 0, need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, p->row_prefix, p->row_prefix, N + 1, st);
+    tmp_bytes = std::max(tmp_bytes, need);
+    int key_bits = 1;
+    while (key_bits < 64 && ((uint64_t)1 << key_bits) < (uint64_t)std::max<int64_t>(1, (int64_t)p->C * p->M)) ++key_bits;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys_a, keys_b, idx_a, idx_b, N, 0, key_bits, st);
+    tmp_bytes = std::max(tmp_bytes, need);
+    cub::DeviceScan::InclusiveSum(nullptr, need, flags, flags, N, st);
+    tmp_bytes = std::max(tmp_bytes, need);
+    BUILD_CUDA(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+    need = tmp_bytes;
+    BUILD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, need, p->row_prefix, p->row_prefix, N + 1, st));
+    int64_t h_total = 0;
+    BUILD_CUDA(cudaMemcpyAsync(&h_total, p->row_prefix + N, 8, cudaMemcpyDeviceToHost, st));
+
+    // --- (camera, pose)-sorted layout -------------------------------------------------------------
+    BUILD_TRY(dev_alloc(&p->s_key, N)); BUILD_TRY(dev_alloc(&p->s_seg, N)); BUILD_TRY(dev_alloc(&p->s_uv, 2 * N));
+    int64_t n_seg = 0;
+    if (N > 0) {
+        PCS_REQUIRE(N < ((int64_t)1 << 31), "n_obs must be below 2^31 per problem (shard by pose across GPUs)");
+        need = tmp_bytes;
+        BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, keys_a, keys_b, idx_a, idx_b, N, 0, key_bits, st));
+        k_segment_flags<<<grid_for(N, 256), 256, 0, st>>>(N, keys_b, flags);
+        need = tmp_bytes;
+        BUILD_CUDA(cub::DeviceScan::InclusiveSum(tmp, need, flags, p->s_seg, N, st));
+        int32_t h_nseg = 0;
+        BUILD_CUDA(cudaMemcpyAsync(&h_nseg, p->s_seg + (N - 1), 4, cudaMemcpyDeviceToHost, st));
+        BUILD_CUDA(cudaStreamSynchronize(st));
+        n_seg = h_nseg;
+    } else {
+        BUILD_CUDA(cudaStreamSynchronize(st));
+    }
+    p->nnz = 2 * h_total;
+    p->n_seg = n_seg;
+    BUILD_TRY(dev_alloc(&p->seg_cam, n_seg)); BUILD_TRY(dev_alloc(&p->seg_pose, n_seg)); BUILD_TRY(dev_alloc(&p->seg_start, n_seg + 1));
+    if (N > 0) {
+        k_segment_fill<<<grid_for(N, 256), 256, 0, st>>>(N, p->M, keys_b, idx_b, p->key, (const double2*)p->uv, p->s_seg,
+                                                         p->s_key, (double2*)p->s_uv, p->seg_cam, p->seg_pose, p->seg_start);
+        BUILD_CUDA(cudaGetLastError());
+    } else {
+        BUILD_CUDA(cudaMemsetAsync(p->seg_start, 0, 8, st));
+    }
+
+    // --- normal-equation outputs: [U | gc | cost | pad | V | gp | W] -------------------------------------
+    const int64_t nU = (int64_t)p->C * 225, ngc = (int64_t)p->C * 15, nV = (int64_t)p->M * 36, ngp = (int64_t)p->M * 6;
+    const int64_t head = (nU + ngc + 1 + 1) / 2 * 2;
+    p->ne_doubles = head + nV + ngp + n_seg * 90;
+    BUILD_TRY(dev_alloc(&p->ne, p->ne_doubles));
+    p->U = p->ne; p->gc = p->U + nU; p->cost = p->gc + ngc; p->V = p->ne + head; p->gp = p->V + nV; p->W = p->gp + ngp;
+
+    // entry table of the v1 normal-equation kernel
+    uint8_t ha[256] = {0}, hb[256] = {0};
+    int e = 0;
+    for (int a = 0; a < NE_COLS; ++a)
+        for (int b = a; b < NE_COLS; ++b) { ha[e] = (uint8_t)a; hb[e] = (uint8_t)b; ++e; }
+    BUILD_CUDA(cudaMemcpyToSymbolAsync(c_ent_a, ha, 256, 0, cudaMemcpyHostToDevice, st));
+    BUILD_CUDA(cudaMemcpyToSymbolAsync(c_ent_b, hb, 256, 0, cudaMemcpyHostToDevice, st));
+    BUILD_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+#undef BUILD_TRY
+#undef BUILD_CUDA
+    return PCS_OK;
+}
+
+int pcs_problem_create(const pcs_problem_desc* d, pcs_problem** out)
+{
+    PCS_REQUIRE(d && out, "desc / out is NULL");
+    *out = nullptr;
+    if (d->chain != PCS_CHAIN_TEMPLATE && d->chain != PCS_CHAIN_SELFCAL) {
+        set_error("unknown chain id; only the two shipped function-block chains are accelerated (no CPU fallback)");
+        return PCS_ERR_CHAIN;
+    }
+    PCS_REQUIRE(d->n_obs >= 0 && d->n_cams > 0 && d->n_poses > 0 && d->n_keys > 0, "sizes must be positive");
+    PCS_REQUIRE(d->n_obs == 0 || (d->cam && d->pose && d->key && d->uv), "observation arrays are NULL");
+    PCS_REQUIRE(d->chain != PCS_CHAIN_TEMPLATE || d->template_xyz, "template chain needs template_xyz");
+    int n_dev = 0;
+    PCS_CUDA(cudaGetDeviceCount(&n_dev));
+    PCS_REQUIRE(d->device >= 0 && d->device < n_dev, "device ordinal out of range");
+    pcs_problem* p = new (std::nothrow) pcs_problem();
+    PCS_REQUIRE(p, "out of host memory");
+    p->chain = d->chain; p->device = d->device; p->N = d->n_obs; p->C = d->n_cams; p->M = d->n_poses; p->K = d->n_keys;
+    p->P = d->chain == PCS_CHAIN_TEMPLATE ? 21 : 24;
+    p->L = 15 * (int64_t)p->C + 6 * (int64_t)p->M + (d->chain == PCS_CHAIN_SELFCAL ? 3 * (int64_t)p->K : 0);
+    int rc = build_problem(p, d);
+    if (rc != PCS_OK) {
+        std::string keep = g_last_error;
+        pcs_problem_destroy(p);
+        set_error(keep);
+        return rc;
+    }
+    *out = p;
+    return PCS_OK;
+}
+
+int pcs_problem_get_info(const pcs_problem* p, pcs_problem_info* info)
+{
+    PCS_REQUIRE(p && info, "NULL argument");
+    info->chain = p->chain; info->n_cams = p->C; info->n_poses = p->M; info->n_keys = p->K; info->cols_per_row = p->P;
+    info->device = p->device; info->n_obs = p->N; info->n_params = p->L; info->n_free = p->n_free; info->nnz = p->nnz;
+    info->n_segments = p->n_seg;
+    return PCS_OK;
+}
+
+int pcs_set_param_string(pcs_problem* p, const double* params)
+{
+    PCS_REQUIRE(p && params, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_TRY(ensure_pinned(p, p->L));
+    std::memcpy(p->h_pin, params, (size_t)p->L * 8);
+    PCS_CUDA(cudaMemcpyAsync(p->params, p->h_pin, (size_t)p->L * 8, cudaMemcpyHostToDevice, p->stream));
+    PCS_CUDA(cudaStreamSynchronize(p->stream));
+    return PCS_OK;
+}
+
+int pcs_get_param_string(pcs_problem* p, double* params)
+{
+    PCS_REQUIRE(p && params, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_CUDA(cudaMemcpyAsync(params, p->params, (size_t)p->L * 8, cudaMemcpyDeviceToHost, p->stream));
+    PCS_CUDA(cudaStreamSynchronize(p->stream));
+    return PCS_OK;
+}
+
+// host x -> device x -> parameter string (x == NULL: keep current parameters)
+static int upload_x(pcs_problem* p, const double* x)
+{
+    if (!x || p->n_free == 0) return PCS_OK;
+    PCS_TRY(ensure_pinned(p, p->n_free));
+    std::memcpy(p->h_pin, x, (size_t)p->n_free * 8);
+    PCS_CUDA(cudaMemcpyAsync(p->x, p->h_pin, (size_t)p->n_free * 8, cudaMemcpyHostToDevice, p->stream));
+    return launch_scatter_x(p, p->x);
+}
+
+int pcs_set_free(pcs_problem* p, const double* x)
+{
+    PCS_REQUIRE(p && x, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_TRY(upload_x(p, x));
+    PCS_CUDA(cudaStreamSynchronize(p->stream));
+    return PCS_OK;
+}
+
+int pcs_residual_dev(pcs_problem* p, const double* x_dev, double* r_dev)
+{
+    PCS_REQUIRE(p && r_dev, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    if (x_dev) PCS_TRY(launch_scatter_x(p, x_dev));
+    PCS_TRY(launch_prepare(p));
+    return launch_residual(p, r_dev);
+}
+
+int pcs_residual(pcs_problem* p, const double* x, double* r_out)
+{
+    PCS_REQUIRE(p && r_out, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    if (!p->resid) PCS_TRY(dev_alloc(&p->resid, 2 * p->N));
+    PCS_TRY(upload_x(p, x));
+    PCS_TRY(launch_prepare(p));
+    PCS_TRY(launch_residual(p, p->resid));
+    if (p->N) PCS_CUDA(cudaMemcpyAsync(r_out, p->resid, (size_t)p->N * 16, cudaMemcpyDeviceToHost, p->stream));
+    PCS_CUDA(cudaStreamSynchronize(p->stream));
+    return PCS_OK;
+}
+
+int pcs_csr_structure(pcs_problem* p, int64_t* col_idx, int64_t* row_ptr)
+{
+    PCS_REQUIRE(p && col_idx && row_ptr, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    int64_t *d_col = nullptr, *d_rp = nullptr;
+    PCS_TRY(dev_alloc(&d_col, p->nnz));
+    int rc = dev_alloc(&d_rp, 2 * p->N + 1);
+    if (rc != PCS_OK) { dev_free(d_col); return rc; }
+    k_csr_structure<<<grid_for(p->N + 1, 256), 256, 0, p->stream>>>(p->N, p->P, p->C, p->M, p->cam, p->pose, p->key,
+                                                                    p->free_map, p->row_prefix, d_col, d_rp);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && p->nnz) e = cudaMemcpyAsync(col_idx, d_col, (size_t)p->nnz * 8, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(row_ptr, d_rp, (size_t)(2 * p->N + 1) * 8, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    dev_free(d_col); dev_free(d_rp);
+    if (e != cudaSuccess) { set_error(std::string("csr structure: ") + cudaGetErrorString(e)); return PCS_ERR_CUDA; }
+    return PCS_OK;
+}
+
+int pcs_jacobian_values_dev(pcs_problem* p, const double* x_dev, double* vals_dev)
+{
+    PCS_REQUIRE(p && vals_dev, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    if (x_dev) PCS_TRY(launch_scatter_x(p, x_dev));
+    PCS_TRY(launch_prepare(p));
+    if (p->N == 0) return PCS_OK;
+    const int grid = grid_for(p->N, 128);
+    const size_t smem = (size_t)4 * 64 * p->P * sizeof(double);
+    if (p->P == 21) {
+        k_jacobian<21><<<grid, 128, smem, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab,
+                                                      p->posetab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
+                                                      p->row_prefix, vals_dev);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) {
+            PCS_CUDA(cudaFuncSetAttribute(k_jacobian<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        k_jacobian<24><<<grid, 128, smem, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab,
+                                                      p->posetab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
+                                                      p->row_prefix, vals_dev);
+    }
+    PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+int pcs_jacobian_values(pcs_problem* p, const double* x, double* vals_out)
+{
+    PCS_REQUIRE(p && vals_out, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    if (!p->jvals) PCS_TRY(dev_alloc(&p->jvals, p->nnz));
+    PCS_TRY(upload_x(p, x));
+    PCS_TRY(pcs_jacobian_values_dev(p, nullptr, p->jvals));
+    if (p->nnz) PCS_CUDA(cudaMemcpyAsync(vals_out, p->jvals, (size_t)p->nnz * 8, cudaMemcpyDeviceToHost, p->stream));
+    PCS_CUDA(cudaStreamSynchronize(p->stream));
+    return PCS_OK;
+}
+
+int pcs_segments(pcs_problem* p, int32_t* seg_cam, int32_t* seg_pose, int64_t* seg_len)
+{
+    PCS_REQUIRE(p, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    const int64_t S = p->n_seg;
+    if (S == 0) return PCS_OK;
+    if (seg_cam) PCS_CUDA(cudaMemcpyAsync(seg_cam, p->seg_cam, (size_t)S * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (seg_pose) PCS_CUDA(cudaMemcpyAsync(seg_pose, p->seg_pose, (size_t)S * 4, cudaMemcpyDeviceToHost, p->stream));
+    std::vector<int64_t> start;
+    if (seg_len) {
+        start.resize(S + 1);
+        PCS_CUDA(cudaMemcpyAsync(start.data(), p->seg_start, (size_t)(S + 1) * 8, cudaMemcpyDeviceToHost, p->stream));
+    }
+    PCS_CUDA(cudaStreamSynchronize(p->stream));
+    if (seg_len) for (int64_t s = 0; s < S; ++s) seg_len[s] = start[s + 1] - start[s];
+    return PCS_OK;
+}
+
+int pcs_normal_equations_dev(pcs_problem* p, const double* x_dev)
+{
+    PCS_REQUIRE(p, "NULL argument");
+    if (p->chain != PCS_CHAIN_TEMPLATE) {
+        set_error("block normal equations are implemented for the template chain; use pcs_normal_dense for the self-calibration chain");
+        return PCS_ERR_UNSUPPORTED;
+    }
+    PCS_CUDA(cudaSetDevice(p->device));
+    if (x_dev) PCS_TRY(launch_scatter_x(p, x_dev));
+    PCS_TRY(launch_prepare(p));
+    return launch_normal_blocks(p);
+}
+
+int pcs_normal_equations(pcs_problem* p, const double* x, double* U, double* gc, double* V, double* gp, double* W,
+                         double* cost)
+{
+    PCS_REQUIRE(p, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_TRY(upload_x(p, x));
+    PCS_TRY(pcs_normal_equations_dev(p, nullptr));
+    cudaStream_t st = p->stream;
+    if (U) PCS_CUDA(cudaMemcpyAsync(U, p->U, (size_t)p->C * 225 * 8, cudaMemcpyDeviceToHost, st));
+    if (gc) PCS_CUDA(cudaMemcpyAsync(gc, p->gc, (size_t)p->C * 15 * 8, cudaMemcpyDeviceToHost, st));
+    if (V) PCS_CUDA(cudaMemcpyAsync(V, p->V, (size_t)p->M * 36 * 8, cudaMemcpyDeviceToHost, st));
+    if (gp) PCS_CUDA(cudaMemcpyAsync(gp, p->gp, (size_t)p->M * 6 * 8, cudaMemcpyDeviceToHost, st));
+    if (W && p->n_seg) PCS_CUDA(cudaMemcpyAsync(W, p->W, (size_t)p->n_seg * 90 * 8, cudaMemcpyDeviceToHost, st));
+    if (cost) PCS_CUDA(cudaMemcpyAsync(cost, p->cost, 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+// dense normal equations at the current parameters, left on the device in p->dense = [JtJ | Jtr | cost]
+int pcs_normal_dense_dev_internal(pcs_problem* p)
+{
+    const int64_t n = p->n_free;
+    PCS_REQUIRE(n > 0 && n <= 32768, "dense normal equations need 0 < n_free <= 32768");
+    if (!p->dense) PCS_TRY(dev_alloc(&p->dense, n * n + n + 1));
+    PCS_TRY(launch_prepare(p));
+    cudaStream_t st = p->stream;
+    PCS_CUDA(cudaMemsetAsync(p->dense, 0, (size_t)(n * n + n + 1) * 8, st));
+    double *dJ = p->dense, *dg = p->dense + n * n, *dc = dg + n;
+    if (p->N) {
+        if (p->P == 21)
+            k_normal_dense<21><<<grid_for(p->N, 128), 128, 0, st>>>(p->N, p->C, p->M, n, p->cam, p->pose, p->key,
+                                                                    (const double2*)p->uv, p->camtab, p->posetab,
+                                                                    points_ptr(p), p->free_map, dJ, dg, dc);
+        else
+            k_normal_dense<24><<<grid_for(p->N, 128), 128, 0, st>>>(p->N, p->C, p->M, n, p->cam, p->pose, p->key,
+                                                                    (const double2*)p->uv, p->camtab, p->posetab,
+                                                                    points_ptr(p), p->free_map, dJ, dg, dc);
+        PCS_CUDA(cudaGetLastError());
+    }
+    k_symmetrize_blocks<<<grid_for(n * n, 256), 256, 0, st>>>(1, (int)n, dJ);
+    PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+int pcs_normal_dense(pcs_problem* p, const double* x, double* JtJ, double* Jtr, double* cost)
+{
+    PCS_REQUIRE(p && JtJ && Jtr && cost, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_TRY(upload_x(p, x));
+    PCS_TRY(pcs_normal_dense_dev_internal(p));
+    const int64_t n = p->n_free;
+    cudaStream_t st = p->stream;
+    double *dJ = p->dense, *dg = p->dense + n * n, *dc = dg + n;
+    PCS_CUDA(cudaMemcpyAsync(JtJ, dJ, (size_t)(n * n) * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaMemcpyAsync(Jtr, dg, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaMemcpyAsync(cost, dc, 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_device_buffers_get(pcs_problem* p, pcs_device_buffers* out)
+{
+    PCS_REQUIRE(p && out, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    if (!p->resid) PCS_TRY(dev_alloc(&p->resid, 2 * p->N));
+    out->params = p->params; out->U = p->U; out->gc = p->gc; out->V = p->V; out->gp = p->gp; out->W = p->W;
+    out->cost = p->cost; out->residual = p->resid; out->stream = (void*)p->stream;
+    return PCS_OK;
+}
+
+int pcs_set_allreduce(pcs_problem* p, pcs_allreduce_fn fn, void* user, int rank, int world_size)
+{
+    PCS_REQUIRE(p, "NULL argument");
+    PCS_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "rank / world_size out of range");
+    p->allreduce = world_size > 1 ? fn : nullptr;
+    p->allreduce_user = user;
+    p->rank = rank;
+    p->world = world_size;
+    return PCS_OK;
+}
+
+}  // extern "C"
+
+namespace pcs {
+// v1 is the default until the tiled kernel lands
+__attribute__((weak)) int launch_normal_blocks(pcs_problem* p) { return launch_normal_blocks_v1(p); }
+__attribute__((weak)) void lm_free(pcs_problem*) {}
+}  // namespace pcs

@@ -1,0 +1,97 @@
+// pcs_internal.cuh -- host-side problem state shared by the translation units of libpcs_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pcs_b200.h"
+
+namespace pcs {
+
+void set_error(const std::string& msg);
+
+#define PCS_CUDA(call)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            ::pcs::set_error(std::string(#call) + " -> " + cudaGetErrorString(e__) + " (" __FILE__ ":" +      \
+                             std::to_string(__LINE__) + ")");                                                 \
+            return PCS_ERR_CUDA;                                                                             \
+        }                                                                                                    \
+    } while (0)
+
+#define PCS_REQUIRE(cond, msg)                                  \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            ::pcs::set_error(std::string("invalid argument: ") + (msg)); \
+            return PCS_ERR_INVALID;                             \
+        }                                                       \
+    } while (0)
+
+#define PCS_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != PCS_OK) return rc__; \
+    } while (0)
+
+}  // namespace pcs
+
+struct pcs_problem {
+    int chain = 0, C = 0, M = 0, K = 0, P = 21, device = 0, sm_count = 148;
+    int64_t N = 0, L = 0, n_free = 0, nnz = 0, n_seg = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    // observations, original (dd) order
+    int32_t *cam = nullptr, *pose = nullptr, *key = nullptr;
+    double* uv = nullptr;
+    // static tables
+    double* tmpl = nullptr;        // [K][3] chain 0
+    int32_t* free_map = nullptr;   // [L]
+    int32_t* free_idx = nullptr;   // [n_free] parameter-string position of free variable j
+    uint16_t* cam_mask = nullptr;  // [C] bit k set = column k of [intr(9) extr(6)] is free
+    uint8_t* pose_mask = nullptr;  // [M] 6 bits
+    uint8_t* key_mask = nullptr;   // [K] 3 bits (chain 1)
+    int64_t* row_prefix = nullptr; // [N+1] free columns per observation, exclusive prefix sum
+    // dynamic
+    double* params = nullptr;      // [L]
+    double* x = nullptr;           // [n_free]
+    double* camtab = nullptr;      // [C][48]
+    double* posetab = nullptr;     // [M][40]
+    double* resid = nullptr;       // [2N] (allocated on first use)
+    double* jvals = nullptr;       // [nnz] (allocated on first use)
+    // (camera, pose)-sorted layout for the normal equations
+    int32_t *seg_cam = nullptr, *seg_pose = nullptr;  // [S]
+    int64_t* seg_start = nullptr;                      // [S+1] into the sorted observation arrays
+    int32_t *s_key = nullptr, *s_seg = nullptr;        // [N] sorted
+    double* s_uv = nullptr;                            // [N][2] sorted
+    // normal-equation outputs: one allocation [U | gc | cost | pad | V | gp | W]
+    double* ne = nullptr;
+    double *U = nullptr, *gc = nullptr, *cost = nullptr, *V = nullptr, *gp = nullptr, *W = nullptr;
+    int64_t ne_doubles = 0;
+    // dense path
+    double* dense = nullptr;  // [n_free*n_free + n_free + 1]
+    // pinned staging
+    double* h_pin = nullptr;
+    int64_t h_pin_doubles = 0;
+
+    pcs_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    int rank = 0, world = 1;
+
+    // LM workspace (pcs_solver.cu)
+    void* lm_ws = nullptr;
+};
+
+namespace pcs {
+// kernels / launchers implemented in pcs_core.cu, used by pcs_solver.cu
+int launch_scatter_x(pcs_problem* p, const double* x_dev);
+int launch_prepare(pcs_problem* p);
+int launch_residual(pcs_problem* p, double* r_dev);
+int launch_cost_only(pcs_problem* p, double* cost_dev);
+int launch_normal_blocks(pcs_problem* p);
+int ensure_pinned(pcs_problem* p, int64_t doubles);
+void lm_free(pcs_problem* p);
+}  // namespace pcs

@@ -1,0 +1,244 @@
+// pcs_math.cuh -- per-observation device math for the bundle-adjustment chain (FP64).
+//
+// Mirrors the reference blocks (paths relative to the pyCamSet repository):
+//   projection        function_block_implementations.py:21-140  (pinhole + Brown-Conrady, params
+//                     [fx, px, fy, py, k1, k2, p1, p2, k3])
+//   rigidTform3d / extrinsic3D / template_points   :143-211      (X' = R(rvec) X + t)
+//   numba_flat_rodrigues_INPLACE / numba_rodrigues_jac  compiled_helpers.py:197-286
+//   chain product (matflow)  matmul_map.py:147-243:  J = [A | Pm [D_c | I] | Pm R_c [D_m | I] (| Pm R_c R_m)]
+//
+// Not a translation: rotations and their derivatives are hoisted out of the per-observation path
+// into per-camera / per-pose tables (the reference recomputes sin/cos for every observation), and
+// the projection Jacobian is evaluated in normalised coordinates instead of the reference's
+// z**7 / z**8 polynomial form (same function, better conditioned).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pcs {
+
+// Per-camera table row: [q(9) | R(9) | t(3) | dR(27)] = 48 doubles.
+constexpr int CAM_Q = 0, CAM_R = 9, CAM_T = 18, CAM_DR = 21, CAM_STRIDE = 48;
+// Per-pose table row: [R(9) | t(3) | dR(27) | pad] = 40 doubles.
+constexpr int POSE_R = 0, POSE_T = 9, POSE_DR = 12, POSE_STRIDE = 40;
+
+__device__ __forceinline__ void rodrigues(const double r[3], double R[9])
+{
+    const double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    const double theta = sqrt(th2);
+    if (theta < 1e-10) {  // compiled_helpers.py:205-210
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        return;
+    }
+    const double inv = 1.0 / theta;
+    double st, ct;
+    sincos(theta, &st, &ct);
+    const double f = (1.0 - ct) * inv * inv;
+    st *= inv;
+    R[0] = r[0] * r[0] * f + ct;
+    R[4] = r[1] * r[1] * f + ct;
+    R[8] = r[2] * r[2] * f + ct;
+    const double xy = r[0] * r[1] * f, xz = r[0] * r[2] * f, yz = r[1] * r[2] * f;
+    R[1] = xy - r[2] * st; R[3] = xy + r[2] * st;
+    R[2] = xz + r[1] * st; R[6] = xz - r[1] * st;
+    R[5] = yz - r[0] * st; R[7] = yz + r[0] * st;
+}
+
+// out[i*9 + k] = d R_k / d r_i  (OpenCV formula, compiled_helpers.py:237-286)
+__device__ __forceinline__ void rodrigues_jac(const double r[3], double out[27])
+{
+    const double theta = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+    for (int k = 0; k < 27; ++k) out[k] = 0.0;
+    if (theta < 1e-10) {  // so(3) generators, compiled_helpers.py:246-254
+        out[5] = -1; out[7] = 1; out[11] = 1; out[15] = -1; out[19] = -1; out[21] = 1;
+        return;
+    }
+    const double it = 1.0 / theta;
+    double st, ct;
+    sincos(theta, &st, &ct);
+    const double c1 = 1.0 - ct;
+    const double n[3] = {r[0] * it, r[1] * it, r[2] * it};
+    const double rrt[9] = {n[0] * n[0], n[0] * n[1], n[0] * n[2], n[0] * n[1], n[1] * n[1],
+                           n[1] * n[2], n[0] * n[2], n[1] * n[2], n[2] * n[2]};
+    const double rx[9] = {0, -n[2], n[1], n[2], 0, -n[0], -n[1], n[0], 0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double ri = n[i];
+        const double a0 = -st * ri, a1 = (st - 2 * c1 * it) * ri, a2 = c1 * it, a3 = (ct - st * it) * ri,
+                     a4 = st * it;
+        double* o = out + 9 * i;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o[k] = a1 * rrt[k] + a3 * rx[k];
+        o[0] += a0; o[4] += a0; o[8] += a0;
+        // a2 * d(rr^T)/dn_i : row i and column i of the 3x3 get n, the (i,i) entry gets 2 n_i
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            o[3 * i + j] += a2 * n[j];
+            o[3 * j + i] += a2 * n[j];
+        }
+        // a4 * d[n]x/dn_i
+        const int j1 = (i + 1) % 3, j2 = (i + 2) % 3;
+        o[3 * j2 + j1] += a4;
+        o[3 * j1 + j2] -= a4;
+    }
+}
+
+// Forward chain up to camera coordinates.
+struct ObsGeom {
+    double Xt[3], Xw[3], Xc[3];
+};
+
+__device__ __forceinline__ void transform(const double* __restrict__ R, const double* __restrict__ t,
+                                          const double X[3], double Y[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Y[a] = fma(R[3 * a], X[0], fma(R[3 * a + 1], X[1], fma(R[3 * a + 2], X[2], t[a])));
+}
+
+// Projection in normalised coordinates; returns projected (u, v) and the pieces the Jacobian needs.
+struct Proj {
+    double u, v;          // projected pixel
+    double xn, yn, r2;    // normalised coords
+    double xD, yD;        // distorted normalised coords
+    double iz;            // 1 / z
+    double drad;          // d rad / d r2
+    double rad;
+};
+
+__device__ __forceinline__ Proj project(const double* __restrict__ q, const double Xc[3])
+{
+    Proj p;
+    p.iz = 1.0 / Xc[2];
+    p.xn = Xc[0] * p.iz;
+    p.yn = Xc[1] * p.iz;
+    p.r2 = fma(p.xn, p.xn, p.yn * p.yn);
+    const double k1 = q[4], k2 = q[5], p1 = q[6], p2 = q[7], k3 = q[8];
+    p.rad = fma(p.r2, fma(p.r2, fma(p.r2, k3, k2), k1), 1.0);
+    p.drad = fma(p.r2, fma(p.r2, 3.0 * k3, 2.0 * k2), k1);
+    const double xy = p.xn * p.yn;
+    p.xD = fma(p.xn, p.rad, fma(2.0 * p1, xy, p2 * fma(2.0 * p.xn, p.xn, p.r2)));
+    p.yD = fma(p.yn, p.rad, fma(p1, fma(2.0 * p.yn, p.yn, p.r2), 2.0 * p2 * xy));
+    p.u = fma(q[0], p.xD, q[1]);
+    p.v = fma(q[2], p.yD, q[3]);
+    return p;
+}
+
+// Jacobian of one observation in "compressed" form:
+//   Au[5] / Av[5]: d u / d(k1,k2,p1,p2,k3), d v / d(k1,k2,p1,p2,k3)
+//   du/dfx = xD, du/dpx = 1, dv/dfy = yD, dv/dpy = 1, all other intrinsic entries are structural zeros
+//   Pm (2x3) = d(u,v)/dXc;  Bc (2x3) = Pm D_c;  N (2x3) = Pm R_c;  Bm (2x3) = N D_m
+// Dense row layout (matflow column order): [fx px fy py k1 k2 p1 p2 k3 | Bc(3) Pm(3) | Bm(3) N(3) | (N R_m)(3)]
+struct ObsJac {
+    double xD, yD;
+    double Au[5], Av[5];
+    double Pm[6];
+    double Bc[6];
+    double N[6];
+    double Bm[6];
+};
+
+__device__ __forceinline__ void projection_jac(const double* __restrict__ q, const Proj& p, ObsJac& J)
+{
+    const double fx = q[0], fy = q[2], p1 = q[6], p2 = q[7];
+    const double r2 = p.r2, r4 = r2 * r2, r6 = r4 * r2;
+    const double xy2 = 2.0 * p.xn * p.yn;
+    J.xD = p.xD;
+    J.yD = p.yD;
+    const double fxx = fx * p.xn, fyy = fy * p.yn;
+    J.Au[0] = fxx * r2; J.Au[1] = fxx * r4; J.Au[2] = fx * xy2; J.Au[3] = fx * fma(2.0 * p.xn, p.xn, r2); J.Au[4] = fxx * r6;
+    J.Av[0] = fyy * r2; J.Av[1] = fyy * r4; J.Av[2] = fy * fma(2.0 * p.yn, p.yn, r2); J.Av[3] = fy * xy2; J.Av[4] = fyy * r6;
+    // d(xD, yD) / d(xn, yn)
+    const double d2 = 2.0 * p.drad;
+    const double xDx = fma(d2 * p.xn, p.xn, p.rad) + 2.0 * p1 * p.yn + 6.0 * p2 * p.xn;
+    const double xDy = d2 * p.xn * p.yn + 2.0 * p1 * p.xn + 2.0 * p2 * p.yn;
+    const double yDy = fma(d2 * p.yn, p.yn, p.rad) + 6.0 * p1 * p.yn + 2.0 * p2 * p.xn;
+    const double sx = fx * p.iz, sy = fy * p.iz;
+    J.Pm[0] = sx * xDx;
+    J.Pm[1] = sx * xDy;
+    J.Pm[2] = -sx * fma(xDx, p.xn, xDy * p.yn);
+    J.Pm[3] = sy * xDy;  // dyD/dxn == dxD/dyn
+    J.Pm[4] = sy * yDy;
+    J.Pm[5] = -sy * fma(xDy, p.xn, yDy * p.yn);
+}
+
+// D[a][i] = sum_j dR[i*9 + 3a + j] X[j]   (rigidTform3d.compute_jac, function_block_implementations.py:161-169)
+// out (2x3) = L (2x3) * D (3x3), without materialising D in memory.
+__device__ __forceinline__ void left_times_drx(const double L[6], const double* __restrict__ dR, const double X[3],
+                                               double out[6])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double d[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            d[a] = fma(dR[9 * i + 3 * a], X[0], fma(dR[9 * i + 3 * a + 1], X[1], dR[9 * i + 3 * a + 2] * X[2]));
+        out[i] = fma(L[0], d[0], fma(L[1], d[1], L[2] * d[2]));
+        out[3 + i] = fma(L[3], d[0], fma(L[4], d[1], L[5] * d[2]));
+    }
+}
+
+// out (2x3) = L (2x3) * R (3x3 row-major)
+__device__ __forceinline__ void left_times_R(const double L[6], const double* __restrict__ R, double out[6])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        out[i] = fma(L[0], R[i], fma(L[1], R[3 + i], L[2] * R[6 + i]));
+        out[3 + i] = fma(L[3], R[i], fma(L[4], R[3 + i], L[5] * R[6 + i]));
+    }
+}
+
+// Full evaluation of one observation: residual + compressed Jacobian.
+__device__ __forceinline__ void eval_obs(const double* __restrict__ cam, const double* __restrict__ pose,
+                                         const double Xt[3], double u_obs, double v_obs, double res[2], ObsJac& J,
+                                         double Xw_out[3])
+{
+    double Xw[3], Xc[3];
+    transform(pose + POSE_R, pose + POSE_T, Xt, Xw);
+    transform(cam + CAM_R, cam + CAM_T, Xw, Xc);
+    const Proj p = project(cam + CAM_Q, Xc);
+    res[0] = p.u - u_obs;
+    res[1] = p.v - v_obs;
+    projection_jac(cam + CAM_Q, p, J);
+    left_times_drx(J.Pm, cam + CAM_DR, Xw, J.Bc);
+    left_times_R(J.Pm, cam + CAM_R, J.N);
+    left_times_drx(J.N, pose + POSE_DR, Xt, J.Bm);
+    Xw_out[0] = Xw[0]; Xw_out[1] = Xw[1]; Xw_out[2] = Xw[2];
+}
+
+// Residual only.
+__device__ __forceinline__ void eval_residual(const double* __restrict__ cam, const double* __restrict__ pose,
+                                              const double Xt[3], double u_obs, double v_obs, double res[2])
+{
+    double Xw[3], Xc[3];
+    transform(pose + POSE_R, pose + POSE_T, Xt, Xw);
+    transform(cam + CAM_R, cam + CAM_T, Xw, Xc);
+    const Proj p = project(cam + CAM_Q, Xc);
+    res[0] = p.u - u_obs;
+    res[1] = p.v - v_obs;
+}
+
+// Expand the compressed Jacobian into dense matflow rows (P = 21, or 24 with the point block).
+// row 0 = d u / d(.), row 1 = d v / d(.)
+template <int P>
+__device__ __forceinline__ void expand_rows(const ObsJac& J, const double* __restrict__ Rm, double ju[P], double jv[P])
+{
+    ju[0] = J.xD; ju[1] = 1.0; ju[2] = 0.0; ju[3] = 0.0;
+    jv[0] = 0.0; jv[1] = 0.0; jv[2] = J.yD; jv[3] = 1.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { ju[4 + k] = J.Au[k]; jv[4 + k] = J.Av[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ju[9 + k] = J.Bc[k];  jv[9 + k] = J.Bc[3 + k];
+        ju[12 + k] = J.Pm[k]; jv[12 + k] = J.Pm[3 + k];
+        ju[15 + k] = J.Bm[k]; jv[15 + k] = J.Bm[3 + k];
+        ju[18 + k] = J.N[k];  jv[18 + k] = J.N[3 + k];
+    }
+    if (P == 24) {
+        double Bk[6];
+        left_times_R(J.N, Rm, Bk);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { ju[21 + k] = Bk[k]; jv[21 + k] = Bk[3 + k]; }
+    }
+}
+
+}  // namespace pcs

@@ -1,0 +1,583 @@
+// pcs_solver.cu -- Levenberg-Marquardt on the device.
+//
+// Replaces scipy.optimize.least_squares (TRF + LSMR, x_scale='jac') as driven by run_bundle_adjustment
+// (optimisation_handling.py:52-117).  The reference never forms J^T J; here the fused kernel delivers the
+// block normal equations and each LM step is
+//   template chain:  eliminate the pose blocks (batched 6x6 Cholesky), form the reduced camera system
+//                    S = U + lambda D_c - Z Z^T with Z = W L^-T (cuBLAS DSYRK on the dense (15C x 6M) Z),
+//                    [all-reduce S | rhs across ranks], dense Cholesky (cuSOLVER), back-substitute the poses;
+//   self-calibration: dense (n_free x n_free) normal matrix + Cholesky.
+// Marquardt scaling (lambda * diag(J^T J)) plays the role of x_scale='jac'; Nielsen's gain-ratio update
+// drives lambda.  Fixed parameters are rows / columns replaced by the identity.
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "pcs_internal.cuh"
+#include "pcs_math.cuh"
+
+namespace pcs {
+
+struct LmWorkspace {
+    cublasHandle_t blas = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    int64_t nc = 0;          // 15 C
+    int64_t np = 0;          // 6 M
+    double* L = nullptr;     // [M][36] lower Cholesky factors of damped V
+    double* y = nullptr;     // [M][6]  L^-1 b_p
+    double* Z = nullptr;     // [np][nc] column-major (nc rows): W L^-T scattered by (camera, pose)
+    double* red = nullptr;   // [S nc*nc | rhs nc | gc nc | cost 1]  (all-reduce unit)
+    int64_t red_doubles = 0;
+    double* t = nullptr;     // [np] Z^T delta_c
+    double* delta = nullptr; // [Lparams]
+    double* backup = nullptr;// [Lparams]
+    double* scal = nullptr;  // [8] device scalars: pred, |dx|^2, |x|^2, ginf, cost_trial, flag
+    double* work = nullptr;
+    int lwork = 0;
+    int* info = nullptr;
+    // dense path
+    double* H = nullptr;     // [n_free^2 + n_free + 1] = JtJ | Jtr | cost  (aliases p->dense)
+    double* Hd = nullptr;    // damped copy [n_free^2]
+    double* rhs = nullptr;   // [n_free]
+};
+
+#define PCS_BLAS(call)                                                                       \
+    do {                                                                                     \
+        cublasStatus_t s__ = (call);                                                         \
+        if (s__ != CUBLAS_STATUS_SUCCESS) {                                                  \
+            set_error(std::string(#call) + " -> cuBLAS status " + std::to_string((int)s__)); \
+            return PCS_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+#define PCS_SOLVER(call)                                                                       \
+    do {                                                                                       \
+        cusolverStatus_t s__ = (call);                                                         \
+        if (s__ != CUSOLVER_STATUS_SUCCESS) {                                                  \
+            set_error(std::string(#call) + " -> cuSOLVER status " + std::to_string((int)s__)); \
+            return PCS_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// --------------------------------------------------------------------------------------------
+// pose elimination: one thread per pose
+// --------------------------------------------------------------------------------------------
+__global__ void k_lm_pose_factor(int M, double lambda, const double* __restrict__ V, const double* __restrict__ gp,
+                                 const uint8_t* __restrict__ pose_mask, double* __restrict__ Lout, double* __restrict__ yout,
+                                 double* __restrict__ scal)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const unsigned mask = pose_mask[m];
+    double A[6][6], b[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const bool fi = mask & (1u << i);
+        b[i] = fi ? -gp[(int64_t)m * 6 + i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const bool fj = mask & (1u << j);
+            double v = (fi && fj) ? V[(int64_t)m * 36 + i * 6 + j] : 0.0;
+            if (i == j) v = (fi && v > 0.0) ? v + lambda * v : 1.0;  // fixed or unobserved: identity row
+            A[i][j] = v;
+        }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        d = sqrt(d);
+        A[j][j] = d;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double s = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
+            A[i][j] = s * inv;
+        }
+    }
+    if (!ok) scal[5] = 1.0;
+    // y = L^-1 b
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= A[i][k] * b[k];
+        b[i] = s / A[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        yout[(int64_t)m * 6 + i] = b[i];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Lout[(int64_t)m * 36 + i * 6 + j] = (j <= i) ? A[i][j] : 0.0;
+    }
+}
+
+// Z rows of one segment: z = w L^-T  (solve L z^T = w^T), scattered into the dense column-major Z
+__global__ void k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose,
+                               const double* __restrict__ W, const double* __restrict__ L, const uint16_t* __restrict__ cam_mask,
+                               const uint8_t* __restrict__ pose_mask, double* __restrict__ Z)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= S * 15) return;
+    const int64_t s = t / 15;
+    const int a = (int)(t % 15);
+    const int c = seg_cam[s], m = seg_pose[s];
+    const bool row_free = cam_mask[c] & (1u << a);
+    const unsigned pm = pose_mask[m];
+    const double* Lm = L + (int64_t)m * 36;
+    double z[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double w = (row_free && (pm & (1u << i))) ? W[s * 90 + a * 6 + i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) w -= Lm[i * 6 + k] * z[k];
+        z[i] = w / Lm[i * 6 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Z[((int64_t)m * 6 + i) * nc + (int64_t)c * 15 + a] = z[i];
+}
+
+// S = blockdiag(U masked + lambda D), rhs = -gc masked, gc copy (for the convergence test)
+__global__ void k_lm_init_reduced(int C, int64_t nc, double lambda, const double* __restrict__ U, const double* __restrict__ gc,
+                                  const double* __restrict__ cost, const uint16_t* __restrict__ cam_mask, double* __restrict__ Smat,
+                                  double* __restrict__ rhs, double* __restrict__ gcopy, double* __restrict__ cost_out, int rank0)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= C * 225) return;
+    const int c = t / 225, e = t % 225, a = e / 15, b = e % 15;
+    const unsigned mask = cam_mask[c];
+    const bool fa = mask & (1u << a), fb = mask & (1u << b);
+    double v = (fa && fb) ? U[t] : 0.0;
+    if (a == b) {
+        // fixed rows: zero here, set to the identity after the all-reduce (k_lm_fix_diag)
+        v = fa ? v + lambda * v : 0.0;
+        rhs[(int64_t)c * 15 + a] = fa ? -gc[c * 15 + a] : 0.0;
+        gcopy[(int64_t)c * 15 + a] = fa ? gc[c * 15 + a] : 0.0;
+    }
+    Smat[((int64_t)c * 15 + b) * nc + (int64_t)c * 15 + a] = v;
+    if (t == 0) *cost_out = *cost;
+}
+
+// rows whose diagonal is exactly zero after the reduction (fixed, or unobserved by every rank) -> identity
+__global__ void k_lm_fix_diag(int64_t nc, double* __restrict__ Smat)
+{
+    int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (a < nc && Smat[a * nc + a] == 0.0) Smat[a * nc + a] = 1.0;
+}
+
+// delta_p = L^-T (y - t)
+__global__ void k_lm_pose_back(int M, const double* __restrict__ L, const double* __restrict__ y, const double* __restrict__ t,
+                               double* __restrict__ delta_p)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double* Lm = L + (int64_t)m * 36;
+    double v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = y[(int64_t)m * 6 + i] - t[(int64_t)m * 6 + i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double s = v[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s -= Lm[k * 6 + i] * v[k];
+        v[i] = s / Lm[i * 6 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) delta_p[(int64_t)m * 6 + i] = v[i];
+}
+
+// delta (parameter-string layout, template chain): [intr | extr | pose] from delta_c (15 per camera) and delta_p.
+// Also accumulates pred = sum delta (lambda D delta + b), |delta|^2, |x|^2 and |g|_inf of the LOCAL pose part
+// plus (rank 0 only for the replicated camera norms) the camera part; D and b are this rank's partial sums.
+__global__ void k_lm_assemble_delta(int C, int M, double lambda, const double* __restrict__ dc, const double* __restrict__ dp,
+                                    const double* __restrict__ U, const double* __restrict__ gc, const double* __restrict__ V,
+                                    const double* __restrict__ gp, const uint16_t* __restrict__ cam_mask,
+                                    const uint8_t* __restrict__ pose_mask, const double* __restrict__ params,
+                                    double* __restrict__ delta, double* __restrict__ scal, int rank0)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = 15 * (int64_t)C + 6 * (int64_t)M;
+    double pred = 0.0, dx2 = 0.0, x2 = 0.0, ginf = 0.0;
+    if (t < total) {
+        double d, D, g;
+        bool replicated;
+        if (t < 15 * (int64_t)C) {
+            int c, a;
+            if (t < 9 * (int64_t)C) { c = (int)(t / 9); a = (int)(t % 9); }
+            else { c = (int)((t - 9 * (int64_t)C) / 6); a = 9 + (int)((t - 9 * (int64_t)C) % 6); }
+            const bool f = cam_mask[c] & (1u << a);
+            d = f ? dc[c * 15 + a] : 0.0;
+            D = f ? U[c * 225 + a * 16] : 0.0;
+            g = f ? gc[c * 15 + a] : 0.0;
+            replicated = true;
+        } else {
+            const int64_t r = t - 15 * (int64_t)C;
+            const int m = (int)(r / 6), a = (int)(r % 6);
+            const bool f = pose_mask[m] & (1u << a);
+            d = f ? dp[r] : 0.0;
+            D = f ? V[(int64_t)m * 36 + a * 7] : 0.0;
+            g = f ? gp[r] : 0.0;
+            replicated = false;
+        }
+        delta[t] = d;
+        pred = d * (lambda * D * d - g);
+        if (!replicated || rank0) {
+            dx2 = d * d;
+            x2 = params[t] * params[t];
+        }
+        ginf = replicated ? 0.0 : fabs(g);  // camera gradient norm is taken from the all-reduced copy on the host side
+    }
+    // block reduction
+    __shared__ double sh[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pred += __shfl_xor_sync(0xffffffffu, pred, o);
+        dx2 += __shfl_xor_sync(0xffffffffu, dx2, o);
+        x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+        ginf = fmax(ginf, __shfl_xor_sync(0xffffffffu, ginf, o));
+    }
+    if (lane == 0) { sh[0][warp] = pred; sh[1][warp] = dx2; sh[2][warp] = x2; sh[3][warp] = ginf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c2 = 0, g2 = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; c2 += sh[2][w]; g2 = fmax(g2, sh[3][w]); }
+        atomicAdd(scal + 0, a);
+        atomicAdd(scal + 1, b);
+        atomicAdd(scal + 2, c2);
+        // non-negative doubles order like their bit patterns
+        atomicMax((unsigned long long*)(scal + 3), (unsigned long long)__double_as_longlong(g2));
+    }
+}
+
+__global__ void k_axpy_params(int64_t n, const double* __restrict__ delta, double* __restrict__ params)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) params[i] += delta[i];
+}
+
+__global__ void k_max_abs(int64_t n, const double* __restrict__ v, double* __restrict__ out)
+{
+    double m = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(v[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(m));
+}
+
+// dense path: Hd = H + lambda diag(H), rhs = -g ; pred / norms after the solve
+__global__ void k_dense_damp(int64_t n, double lambda, const double* __restrict__ H, const double* __restrict__ g,
+                             double* __restrict__ Hd, double* __restrict__ rhs)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * n) return;
+    const int64_t i = t / n, j = t % n;
+    double v = H[t];
+    if (i == j) {
+        v += lambda * fmax(v, 1e-12);
+        rhs[i] = -g[i];
+    }
+    Hd[t] = v;
+}
+
+__global__ void k_dense_delta(int64_t n, double lambda, const double* __restrict__ d, const double* __restrict__ H,
+                              const double* __restrict__ g, const int32_t* __restrict__ free_idx, const double* __restrict__ params,
+                              double* __restrict__ delta_full, double* __restrict__ scal)
+{
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double pred = 0, dx2 = 0, x2 = 0, ginf = 0;
+    if (j < n) {
+        const double dj = d[j];
+        const int32_t pi = free_idx[j];
+        delta_full[pi] = dj;
+        pred = dj * (lambda * fmax(H[j * n + j], 1e-12) * dj - g[j]);
+        dx2 = dj * dj;
+        x2 = params[pi] * params[pi];
+        ginf = fabs(g[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pred += __shfl_xor_sync(0xffffffffu, pred, o);
+        dx2 += __shfl_xor_sync(0xffffffffu, dx2, o);
+        x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+        ginf = fmax(ginf, __shfl_xor_sync(0xffffffffu, ginf, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(scal + 0, pred);
+        atomicAdd(scal + 1, dx2);
+        atomicAdd(scal + 2, x2);
+        atomicMax((unsigned long long*)(scal + 3), (unsigned long long)__double_as_longlong(ginf));
+    }
+}
+
+__global__ void k_gather_free(int64_t n, const int32_t* __restrict__ free_idx, const double* __restrict__ params, double* __restrict__ x)
+{
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < n) x[j] = params[free_idx[j]];
+}
+
+void lm_free(pcs_problem* p)
+{
+    LmWorkspace* w = (LmWorkspace*)p->lm_ws;
+    if (!w) return;
+    if (w->blas) cublasDestroy(w->blas);
+    if (w->solver) cusolverDnDestroy(w->solver);
+    double* ptrs[] = {w->L, w->y, w->Z, w->red, w->t, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs};
+    for (double* q : ptrs) if (q) cudaFree(q);
+    if (w->info) cudaFree(w->info);
+    delete w;
+    p->lm_ws = nullptr;
+}
+
+static int lm_prepare(pcs_problem* p)
+{
+    if (p->lm_ws) return PCS_OK;
+    LmWorkspace* w = new LmWorkspace();
+    p->lm_ws = w;
+    PCS_BLAS(cublasCreate(&w->blas));
+    PCS_BLAS(cublasSetStream(w->blas, p->stream));
+    PCS_SOLVER(cusolverDnCreate(&w->solver));
+    PCS_SOLVER(cusolverDnSetStream(w->solver, p->stream));
+    PCS_CUDA(cudaMalloc((void**)&w->delta, (size_t)p->L * 8));
+    PCS_CUDA(cudaMalloc((void**)&w->backup, (size_t)p->L * 8));
+    PCS_CUDA(cudaMalloc((void**)&w->scal, 8 * 8));
+    PCS_CUDA(cudaMalloc((void**)&w->info, sizeof(int)));
+    PCS_CUDA(cudaMemsetAsync(w->delta, 0, (size_t)p->L * 8, p->stream));
+    if (p->chain == PCS_CHAIN_TEMPLATE) {
+        w->nc = 15 * (int64_t)p->C;
+        w->np = 6 * (int64_t)p->M;
+        PCS_CUDA(cudaMalloc((void**)&w->L, (size_t)p->M * 36 * 8));
+        PCS_CUDA(cudaMalloc((void**)&w->y, (size_t)w->np * 8));
+        PCS_CUDA(cudaMalloc((void**)&w->t, (size_t)w->np * 8));
+        PCS_CUDA(cudaMalloc((void**)&w->Z, (size_t)(w->nc * w->np) * 8));
+        PCS_CUDA(cudaMemsetAsync(w->Z, 0, (size_t)(w->nc * w->np) * 8, p->stream));  // sparsity pattern is static
+        w->red_doubles = w->nc * w->nc + 2 * w->nc + 1;
+        PCS_CUDA(cudaMalloc((void**)&w->red, (size_t)w->red_doubles * 8));
+        PCS_SOLVER(cusolverDnDpotrf_bufferSize(w->solver, CUBLAS_FILL_MODE_LOWER, (int)w->nc, w->red, (int)w->nc, &w->lwork));
+    } else {
+        const int64_t n = p->n_free;
+        PCS_REQUIRE(n > 0 && n <= 32768, "dense LM path needs 0 < n_free <= 32768");
+        if (!p->dense) PCS_CUDA(cudaMalloc((void**)&p->dense, (size_t)(n * n + n + 1) * 8));
+        w->H = p->dense;
+        PCS_CUDA(cudaMalloc((void**)&w->Hd, (size_t)(n * n) * 8));
+        PCS_CUDA(cudaMalloc((void**)&w->rhs, (size_t)n * 8));
+        PCS_SOLVER(cusolverDnDpotrf_bufferSize(w->solver, CUBLAS_FILL_MODE_LOWER, (int)n, w->Hd, (int)n, &w->lwork));
+    }
+    PCS_CUDA(cudaMalloc((void**)&w->work, (size_t)std::max(w->lwork, 1) * 8));
+    return PCS_OK;
+}
+
+// evaluate the normal equations at the current p->params (tables refreshed)
+static int eval_normal(pcs_problem* p)
+{
+    PCS_TRY(launch_prepare(p));
+    if (p->chain == PCS_CHAIN_TEMPLATE) return launch_normal_blocks(p);
+    return PCS_ERR_UNSUPPORTED;
+}
+
+// One damped solve at the current linearisation.  On return w->delta holds the step (parameter-string layout)
+// and h_scal = {pred, |dx|^2, |x|^2, |g_pose|_inf, -, flag}.
+static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda, double* h_scal, double* h_ginf_cam, double* h_cost)
+{
+    cudaStream_t st = p->stream;
+    const int64_t nc = w->nc, np = w->np;
+    double* Smat = w->red;
+    double* rhs = w->red + nc * nc;
+    double* gcopy = rhs + nc;
+    double* cost_r = gcopy + nc;
+    PCS_CUDA(cudaMemsetAsync(w->scal, 0, 8 * 8, st));
+    PCS_CUDA(cudaMemsetAsync(Smat, 0, (size_t)(nc * nc) * 8, st));
+    k_lm_pose_factor<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, lambda, p->V, p->gp, p->pose_mask, w->L, w->y, w->scal);
+    if (p->n_seg)
+        k_lm_segment_Z<<<grid_for(p->n_seg * 15, 256), 256, 0, st>>>(p->n_seg, nc, p->seg_cam, p->seg_pose, p->W, w->L,
+                                                                     p->cam_mask, p->pose_mask, w->Z);
+    k_lm_init_reduced<<<grid_for((int64_t)p->C * 225, 256), 256, 0, st>>>(p->C, nc, lambda, p->U, p->gc, p->cost, p->cam_mask,
+                                                                        Smat, rhs, gcopy, cost_r, p->rank == 0);
+    PCS_CUDA(cudaGetLastError());
+    const double minus1 = -1.0, one = 1.0, zero = 0.0;
+    PCS_BLAS(cublasDsyrk(w->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, &one, Smat, (int)nc));
+    PCS_BLAS(cublasDgemv(w->blas, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, w->y, 1, &one, rhs, 1));
+    if (p->allreduce) {
+        int rc = p->allreduce(p->allreduce_user, w->red, w->red_doubles, 0, (void*)st);
+        if (rc != 0) { set_error("all-reduce callback failed"); return PCS_ERR_CUDA; }
+    }
+    k_lm_fix_diag<<<grid_for(nc, 256), 256, 0, st>>>(nc, Smat);
+    PCS_SOLVER(cusolverDnDpotrf(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, Smat, (int)nc, w->work, w->lwork, w->info));
+    PCS_SOLVER(cusolverDnDpotrs(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, 1, Smat, (int)nc, rhs, (int)nc, w->info));
+    // rhs now holds delta_c
+    PCS_BLAS(cublasDgemv(w->blas, CUBLAS_OP_T, (int)nc, (int)np, &one, w->Z, (int)nc, rhs, 1, &zero, w->t, 1));
+    double* dp = w->delta + 15 * (int64_t)p->C;  // pose part of the parameter-string delta is written in place
+    k_lm_pose_back<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, w->L, w->y, w->t, dp);
+    k_lm_assemble_delta<<<grid_for(15 * (int64_t)p->C + 6 * (int64_t)p->M, 128), 128, 0, st>>>(
+        p->C, p->M, lambda, rhs, dp, p->U, p->gc, p->V, p->gp, p->cam_mask, p->pose_mask, p->params, w->delta, w->scal, p->rank == 0);
+    k_max_abs<<<std::max(1, std::min(64, grid_for(nc, 256))), 256, 0, st>>>(nc, gcopy, w->scal + 4);
+    PCS_CUDA(cudaGetLastError());
+    if (p->allreduce) {  // pred, |dx|^2, |x|^2 are partial sums over this rank's poses; the pose gradient norm is a max
+        if (p->allreduce(p->allreduce_user, w->scal, 3, 0, (void*)st) != 0 ||
+            p->allreduce(p->allreduce_user, w->scal + 3, 1, 1, (void*)st) != 0) {
+            set_error("all-reduce callback failed");
+            return PCS_ERR_CUDA;
+        }
+    }
+    int h_info = 0;
+    PCS_CUDA(cudaMemcpyAsync(h_scal, w->scal, 8 * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaMemcpyAsync(&h_info, w->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaMemcpyAsync(h_cost, cost_r, 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    *h_ginf_cam = h_scal[4];
+    if (h_info != 0 || h_scal[5] != 0.0) return PCS_ERR_NUMERIC;
+    return PCS_OK;
+}
+
+}  // namespace pcs
+
+using namespace pcs;
+
+extern "C" {
+
+void pcs_lm_default_options(pcs_lm_options* o)
+{
+    if (!o) return;
+    o->max_iter = 100;
+    o->verbose = 0;
+    o->lambda0 = 1e-3;
+    o->ftol = o->xtol = o->gtol = 1e-8;
+    o->lambda_min = 1e-12;
+    o->lambda_max = 1e12;
+}
+
+// dense normal equations at the current parameters, device-resident (pcs_core.cu)
+int pcs_normal_dense_dev_internal(pcs_problem* p);
+
+int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in, double* x_out, pcs_lm_stats* stats)
+{
+    PCS_REQUIRE(p && x_out, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    pcs_lm_options o;
+    if (opts_in) o = *opts_in; else pcs_lm_default_options(&o);
+    PCS_TRY(lm_prepare(p));
+    LmWorkspace* w = (LmWorkspace*)p->lm_ws;
+    cudaStream_t st = p->stream;
+    cudaEvent_t ev0, ev1;
+    PCS_CUDA(cudaEventCreate(&ev0));
+    PCS_CUDA(cudaEventCreate(&ev1));
+    PCS_CUDA(cudaEventRecord(ev0, st));
+    if (x0) {
+        PCS_TRY(ensure_pinned(p, std::max<int64_t>(p->n_free, 1)));
+        std::memcpy(p->h_pin, x0, (size_t)p->n_free * 8);
+        PCS_CUDA(cudaMemcpyAsync(p->x, p->h_pin, (size_t)p->n_free * 8, cudaMemcpyHostToDevice, st));
+        PCS_TRY(launch_scatter_x(p, p->x));
+    }
+    const bool tmpl = p->chain == PCS_CHAIN_TEMPLATE;
+    const int64_t n = p->n_free;
+    int n_normal = 0, n_cost = 0, status = 0, it = 0;
+    double lambda = o.lambda0, nu = 2.0;
+    double cost = 0.0, cost0 = 0.0, ginf = 0.0;
+    double h_scal[8] = {0};
+
+    auto eval_lin = [&]() -> int {  // normal equations at p->params; returns r.r in `cost`
+        ++n_normal;
+        if (tmpl) return eval_normal(p);
+        return pcs_normal_dense_dev_internal(p);
+    };
+    int rc = eval_lin();
+    bool have_cost = false;
+    while (rc == PCS_OK && it < o.max_iter) {
+        ++it;
+        double ginf_cam = 0.0, cost_lin = 0.0;
+        if (tmpl) {
+            rc = solve_template(p, w, lambda, h_scal, &ginf_cam, &cost_lin);
+        } else {
+            double *H = w->H, *g = w->H + n * n, *c = g + n;
+            PCS_CUDA(cudaMemsetAsync(w->scal, 0, 8 * 8, st));
+            k_dense_damp<<<grid_for(n * n, 256), 256, 0, st>>>(n, lambda, H, g, w->Hd, w->rhs);
+            PCS_SOLVER(cusolverDnDpotrf(w->solver, CUBLAS_FILL_MODE_LOWER, (int)n, w->Hd, (int)n, w->work, w->lwork, w->info));
+            PCS_SOLVER(cusolverDnDpotrs(w->solver, CUBLAS_FILL_MODE_LOWER, (int)n, 1, w->Hd, (int)n, w->rhs, (int)n, w->info));
+            k_dense_delta<<<grid_for(n, 128), 128, 0, st>>>(n, lambda, w->rhs, H, g, p->free_idx, p->params, w->delta, w->scal);
+            int h_info = 0;
+            PCS_CUDA(cudaMemcpyAsync(h_scal, w->scal, 8 * 8, cudaMemcpyDeviceToHost, st));
+            PCS_CUDA(cudaMemcpyAsync(&h_info, w->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PCS_CUDA(cudaMemcpyAsync(&cost_lin, c, 8, cudaMemcpyDeviceToHost, st));
+            PCS_CUDA(cudaStreamSynchronize(st));
+            if (h_info != 0) rc = PCS_ERR_NUMERIC;
+        }
+        if (rc == PCS_ERR_NUMERIC) {  // not positive definite at this damping: raise lambda and retry
+            rc = PCS_OK;
+            lambda = std::min(lambda * 10.0, o.lambda_max);
+            if (lambda >= o.lambda_max) { status = -1; break; }
+            continue;
+        }
+        if (rc != PCS_OK) break;
+        if (!have_cost) { cost = cost0 = cost_lin; have_cost = true; }
+        ginf = std::max(ginf_cam, h_scal[3]);
+        if (ginf < o.gtol) { status = 1; break; }
+        const double pred = h_scal[0], dx = std::sqrt(h_scal[1]), xn = std::sqrt(h_scal[2]);
+        if (dx < o.xtol * (o.xtol + xn)) { status = 3; break; }
+        // trial point
+        PCS_CUDA(cudaMemcpyAsync(w->backup, p->params, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
+        k_axpy_params<<<grid_for(p->L, 256), 256, 0, st>>>(p->L, w->delta, p->params);
+        PCS_TRY(launch_prepare(p));
+        PCS_TRY(launch_cost_only(p, w->scal + 6));
+        double cost_new = 0.0;
+        ++n_cost;
+        if (p->allreduce && p->allreduce(p->allreduce_user, w->scal + 6, 1, 0, (void*)st) != 0) {
+            set_error("all-reduce callback failed");
+            rc = PCS_ERR_CUDA;
+            break;
+        }
+        PCS_CUDA(cudaMemcpyAsync(&cost_new, w->scal + 6, 8, cudaMemcpyDeviceToHost, st));
+        PCS_CUDA(cudaStreamSynchronize(st));
+        const double actual = cost - cost_new;          // in units of r.r
+        const double rho = (pred > 0.0 && std::isfinite(cost_new)) ? actual / pred : -1.0;
+        if (o.verbose)
+            std::fprintf(stderr, "[pcs lm] it %3d  cost %.9e  trial %.9e  rho %8.3g  lambda %.2e  |g| %.2e  |dx| %.2e\n", it,
+                         0.5 * cost, 0.5 * cost_new, rho, lambda, ginf, dx);
+        if (rho > 0.0) {
+            const double rel = actual / std::max(cost, 1e-300);
+            cost = cost_new;
+            const double f = 1.0 - std::pow(2.0 * rho - 1.0, 3.0);
+            lambda = std::max(o.lambda_min, lambda * std::max(1.0 / 3.0, f));
+            nu = 2.0;
+            rc = eval_lin();
+            if (rc != PCS_OK) break;
+            if (rel < o.ftol) { status = 2; break; }
+        } else {
+            PCS_CUDA(cudaMemcpyAsync(p->params, w->backup, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
+            lambda = std::min(o.lambda_max, lambda * nu);
+            nu *= 2.0;
+            if (lambda >= o.lambda_max) { status = -1; break; }
+        }
+    }
+    if (rc == PCS_OK) {
+        PCS_TRY(launch_prepare(p));
+        if (n) {
+            k_gather_free<<<grid_for(n, 256), 256, 0, st>>>(n, p->free_idx, p->params, p->x);
+            PCS_CUDA(cudaMemcpyAsync(x_out, p->x, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    PCS_CUDA(cudaEventRecord(ev1, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (stats) {
+        stats->iterations = it; stats->n_eval_normal = n_normal; stats->n_eval_cost = n_cost; stats->status = status;
+        stats->cost_initial = 0.5 * cost0; stats->cost_final = 0.5 * cost; stats->grad_norm_inf = ginf;
+        stats->lambda_final = lambda; stats->seconds = ms * 1e-3;
+    }
+    return rc;
+}
+
+}  // extern "C"
