@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the bundle-adjustment hot path on B200 (contract: see DESIGN.md "Measurement").
+
+One "step" = one evaluation of residual + analytic Jacobian + J^T J / J^T r (block normal equations) at a
+fixed parameter vector over this rank's observation shard, plus (N > 1) the NCCL all-reduce of the camera
+blocks.  Metric: Mobs/s (whole job, all ranks).
+
+    python bench.py                              # N = 1, config 4: 32-camera ring x 2000 poses
+    torchrun ... bench.py --gpus N               # weak scaling: 32-camera ring x 2000 poses PER GPU, sharded by pose
+    python bench.py --workload dome128           # config 5 (strong scaling across --gpus): 128-camera dome x 20000 poses
+    python bench.py --impl reference             # CPU arm: the oracle port of the reference path on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Mobs/s residual+Jacobian+JtJ eval"
+ALGO_BYTES_PER_OBS = 28.0  # (u, v) 16 B + cam, pose, key 12 B; K_ne writes O(params), not O(N)
+
+WORKLOADS = {
+    # name: (layout, n_cams, poses, detect_prob, scaling)
+    "ring32": ("ring", 32, 2000, 1.0, "weak"),      # config 4; poses are PER GPU
+    "dome128": ("dome", 128, 20000, 0.5, "strong"),  # config 5; poses are the job total
+    "ring8": ("ring", 8, 100, 1.0, "weak"),         # config 1 (parity-sized; for quick runs)
+}
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_shard(args, rank, world, device):
+    """Synthetic observations of this rank's pose shard, generated directly in HBM."""
+    import torch
+    from pycamset_b200 import synthetic as syn
+    from pycamset_b200.distributed import even_pose_ranges
+
+    layout, n_cams, poses, detect_prob, scaling = WORKLOADS[args.workload]
+    if args.poses:
+        poses = args.poses
+    total_poses = poses * world if scaling == "weak" else poses
+    p0, p1 = even_pose_ranges(total_poses, world)[rank]
+    rig = syn.make_rig(n_cams, total_poses, layout=layout, distortion=True, seed=args.seed, detect_prob=detect_prob,
+                       pose_start=p0, pose_stop=p1, device=device, order="cam")
+    rng = np.random.default_rng(args.seed + 1)
+    intr, extr, posesp = rig.perturbed(rng, 1e-3)
+    m_local = p1 - p0
+    params = np.concatenate([intr.ravel(), extr.ravel(), posesp[p0:p1].ravel()])
+    unfixed = np.ones(params.shape[0], bool)
+    if p0 == 0:
+        unfixed[15 * n_cams:15 * n_cams + 6] = False  # pose 0 is the gauge (template_handler.py:134-137)
+    pose_local = (rig.pose - p0).to(torch.int32)
+    return dict(rig=rig, cam=rig.cam, pose=pose_local, key=rig.key, uv=rig.uv, n_cams=n_cams, n_poses=m_local,
+                params=params, unfixed=unfixed, total_poses=total_poses, scaling=scaling, layout=layout,
+                detect_prob=detect_prob)
+
+
+def oracle_eval_mobs(sh, max_obs, min_seconds, threads=None):
+    """Time the CPU restatement (oracle port of the reference path) on a bounded sample of the workload:
+    residual + CSR Jacobian values + block J^T J / J^T r.  Returns (Mobs/s, n_obs_sample, cores, passes)."""
+    from oracle import oracle as orc
+    if threads:
+        orc.set_threads(threads)
+    cores = orc.num_threads()
+    n = min(int(sh["cam"].shape[0]), max_obs)
+    cam = sh["cam"][:n].cpu().numpy(); pose = sh["pose"][:n].cpu().numpy(); key = sh["key"][:n].cpu().numpy()
+    uv = sh["uv"][:n].cpu().numpy()
+    C, M = sh["n_cams"], sh["n_poses"]
+    o = orc.Problem(0, cam, pose, key, uv, C, M, 81, sh["rig"].template)
+    fm = orc.free_map_from_mask(sh["unfixed"])
+    col, rp = o.csr_structure(fm)            # static structure: built once, like the reference (not timed)
+    pair = cam.astype(np.int64) * M + pose
+    _, seg = np.unique(pair, return_inverse=True)
+    seg = seg.astype(np.int32); n_seg = int(seg.max()) + 1 if n else 0
+    params = sh["params"]
+
+    def one_pass():
+        o.residual(params)
+        o.csr_values(params, fm, rp)
+        o.normal_blocks(params, seg, n_seg)
+
+    one_pass()  # warm-up
+    best, passes, t_all = float("inf"), 0, time.perf_counter()
+    while passes < 3 or (time.perf_counter() - t_all) < min_seconds:
+        t0 = time.perf_counter(); one_pass(); dt = time.perf_counter() - t0
+        best = min(best, dt); passes += 1
+        if passes >= 200:
+            break
+    return n / best / 1e6, n, cores, passes
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference path's CPU implementation (oracle port; the reference itself is Python +
+    numba and does not travel to the GPU box) on all host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    sh = build_shard(args, 0, 1, "cpu")
+    t0 = time.perf_counter()
+    vals = []
+    for step in range(args.warmup + args.steps):
+        mobs, n, cores, passes = oracle_eval_mobs(sh, args.cpu_sample_obs, 0.0)
+        if step >= args.warmup:
+            vals.append(mobs)
+    v = float(np.mean(vals))
+    sample = f"first {n} observations of {args.workload} (cam-major order), best of {passes} passes per step"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mobs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": n / v / 1e3, "higher_is_better": True,
+        "scaling": WORKLOADS[args.workload][4], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, sh, world),
+        "cpu_baseline": {"value": v, "unit": "Mobs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, sh, world):
+    layout, n_cams, poses, detect_prob, scaling = WORKLOADS[args.workload]
+    return {
+        "workload": f"{n_cams}-camera {layout} x {sh['total_poses']} poses, ChArUco(10,10,4) 81 pts, radial+tangential "
+                    f"distortion, template chain (P=21)",
+        "n_cams": n_cams, "n_poses_total": sh["total_poses"], "poses_per_gpu": sh["n_poses"],
+        "detect_prob": detect_prob, "sharding": f"by pose, {world} rank(s)", "seed": args.seed,
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ring32", choices=sorted(WORKLOADS))
+    ap.add_argument("--poses", type=int, default=0, help="override the workload's pose count")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample-obs", type=int, default=1_000_000)
+    ap.add_argument("--no-lm", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lm-iters", type=int, default=10)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pycamset_b200.problem import BundleProblem
+    from pycamset_b200 import distributed as pdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
+
+    t_setup = time.perf_counter()
+    sh = build_shard(args, rank, world, f"cuda:{dev}")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize(dev)
+    prob = BundleProblem(0, sh["cam"], sh["pose"], sh["key"], sh["uv"], sh["n_cams"], sh["n_poses"], 81,
+                         template=sh["rig"].template, unfixed=sh["unfixed"], device=dev, stream=stream.cuda_stream)
+    prob.set_param_string(sh["params"])
+    x_host = torch.from_numpy(sh["params"][sh["unfixed"]].copy()).pin_memory()
+    x_dev = x_host.to(f"cuda:{dev}")
+    n_local = prob.n_obs
+    setup_s = time.perf_counter() - t_setup
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+
+    def step():
+        prob.normal_equations_device(x_dev.data_ptr())
+        if world > 1:
+            pdist.allreduce_camera_blocks(prob)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush_buf.zero_()
+            step()
+        barrier()
+        prob.timing_enable(True)
+        sampler = ClockSampler(dev)
+        if rank == 0:
+            sampler.start()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        kern_ms = []
+        barrier()
+        t_wall = time.perf_counter()
+        for k in range(args.steps):
+            flush_buf.zero_()                 # L2 flush, outside the per-step event pair
+            starts[k].record(stream)
+            step()
+            ends[k].record(stream)
+            kern_ms.append(prob.timing_normal_kernel_ms())
+        barrier()
+        wall_s = time.perf_counter() - t_wall
+        clocks = sampler.stop() if rank == 0 else None
+        prob.timing_enable(False)
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(np.sum(step_ms))
+    n_total = n_local
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        c = torch.tensor([n_local], dtype=torch.int64, device=f"cuda:{dev}")
+        dist.all_reduce(c)
+        n_total = int(c.item())
+    ms_per_step = total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end-to-end through the host-facing C-ABI call: host x in, all blocks out to (pinned) host memory -------
+    C, M, S = prob.n_cams, prob.n_poses, prob.n_segments
+    def pinned(*shape):
+        return torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    outb = dict(U=pinned(C, 15, 15), gc=pinned(C, 15), V=pinned(M, 6, 6), gp=pinned(M, 6), W=pinned(S, 15, 6),
+                cost_buf=pinned(1))
+    xh = x_host.numpy()
+    h2d = int(xh.nbytes)
+    d2h = int(sum(v.nbytes for v in outb.values()))
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            prob.normal_equations(xh, out=outb)
+        e2e_steps = max(3, min(args.steps, 10))
+        barrier()
+        e2e_s = 0.0
+        for _ in range(e2e_steps):
+            flush_buf.zero_()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            prob.normal_equations(xh, out=outb)   # H2D x, kernels, D2H blocks, stream sync
+            if world > 1:
+                pass  # host-resident blocks of different ranks are combined by the caller; not part of this call
+            e2e_s += time.perf_counter() - t0
+        barrier()
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = n_total / (float(e2e_t.item()) / e2e_steps) / 1e6
+
+    # ---- LM iterations / s (device-resident solve; all-reduce of the reduced camera system for N > 1) --------------
+    lm = None
+    if not args.no_lm:
+        try:
+            if world > 1:
+                pdist.install_nccl_allreduce(prob)
+            prob.set_param_string(sh["params"])
+            with torch.cuda.stream(stream):
+                prob.lm_solve(xh, max_iter=2, ftol=0, xtol=0, gtol=0)        # warm-up (workspace, cuBLAS / cuSOLVER init)
+                prob.set_param_string(sh["params"])
+                barrier()
+                _, st = prob.lm_solve(xh, max_iter=args.lm_iters, ftol=0, xtol=0, gtol=0)
+                barrier()
+            secs = torch.tensor([st["seconds"]], dtype=torch.float64, device=f"cuda:{dev}")
+            if world > 1:
+                dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+            lm = {"iter_per_s": st["iterations"] / float(secs.item()), "iterations": st["iterations"],
+                  "cost_initial": st["cost_initial"], "cost_final": st["cost_final"], "status": st["status"]}
+        except Exception as e:  # report, never hide
+            lm = {"error": str(e)[:200]}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kern_avg_ms = float(np.mean(kern_ms))
+        achieved = ALGO_BYTES_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get(args.workload)
+            except Exception:
+                traffic = None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            mobs, n_s, cores, passes = oracle_eval_mobs(sh, args.cpu_sample_obs, 10.0)
+            cpu = {"value": mobs, "unit": "Mobs/s", "cores": cores, "kind": "port",
+                   "sample": f"first {n_s} observations of the same workload; residual + CSR Jacobian + block JtJ/Jtr, "
+                             f"best of {passes} passes"}
+        out = {
+            "metric": METRIC, "value": value, "unit": "Mobs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": sh["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {**workload_config(args, sh, world), "n_obs_total": n_total, "n_obs_per_gpu": n_local,
+                       "n_segments_per_gpu": prob.n_segments, "n_free_per_gpu": prob.n_free},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "normal-equation kernel (K_ne)",
+                         "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_obs": ALGO_BYTES_PER_OBS,
+                         "note": "FP64-ALU bound by design (SURVEY.md 7): see DESIGN.md for the FP64 roof"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Mobs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "call": "BundleProblem.normal_equations(x_host) -> U, gc, V, gp, W, cost on host"},
+            "gpu_launches": args.steps * 5, "clocks": clocks, "lm": lm,
+            "setup_s": setup_s, "wall_s_timed_region": wall_s,
+        }
+        print(json.dumps(out), flush=True)
+    prob.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,11 @@ PCS_API void pcs_lm_default_options(pcs_lm_options* o);
 PCS_API int pcs_lm_solve(pcs_problem* p, const double* x0 /*[n_free]*/, const pcs_lm_options* opts,
                          double* x_out /*[n_free]*/, pcs_lm_stats* stats);
 
+/* Optional kernel timing: when enabled, the fused normal-equation kernel is bracketed by CUDA events on the
+ * problem's stream; pcs_timing_get returns the duration (ms) of its most recent launch (synchronises). */
+PCS_API int pcs_timing_enable(pcs_problem* p, int on);
+PCS_API int pcs_timing_get(pcs_problem* p, double* normal_kernel_ms);
+
 /* Library / device probe: returns the device's SM count, or a negative pcs_status. */
 PCS_API int pcs_device_sm_count(int device);
 PCS_API const char* pcs_version(void);

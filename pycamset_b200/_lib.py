@@ -20,7 +20,8 @@ EXPORTED_SYMBOLS = [
     "pcs_set_param_string", "pcs_set_free", "pcs_get_param_string", "pcs_residual", "pcs_residual_dev",
     "pcs_csr_structure", "pcs_jacobian_values", "pcs_jacobian_values_dev", "pcs_segments", "pcs_normal_equations",
     "pcs_normal_equations_dev", "pcs_normal_dense", "pcs_device_buffers_get", "pcs_set_allreduce",
-    "pcs_lm_default_options", "pcs_lm_solve", "pcs_device_sm_count", "pcs_version",
+    "pcs_lm_default_options", "pcs_lm_solve", "pcs_timing_enable", "pcs_timing_get", "pcs_device_sm_count",
+    "pcs_version",
 ]
 
 
@@ -108,6 +109,8 @@ def load() -> ct.CDLL:
     lib.pcs_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, ct.c_int, ct.c_int]
     lib.pcs_lm_default_options.argtypes = [ct.POINTER(LmOptions)]
     lib.pcs_lm_solve.argtypes = [vp, vp, ct.POINTER(LmOptions), vp, ct.POINTER(LmStats)]
+    lib.pcs_timing_enable.argtypes = [vp, ct.c_int]
+    lib.pcs_timing_get.argtypes = [vp, ct.POINTER(ct.c_double)]
     lib.pcs_device_sm_count.argtypes = [ct.c_int]
     _lib = lib
     return lib

@@ -393,10 +393,12 @@ int launch_normal_blocks_v1(pcs_problem* p)
         int64_t per = ((p->N + warps - 1) / warps + 31) / 32 * 32;
         warps = (p->N + per - 1) / per;
         int grid = (int)((warps + 3) / 4);
+        if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a, p->stream));
         k_normal_v1<<<grid, 128, 0, p->stream>>>(p->N, per, p->s_key, (const double2*)p->s_uv, p->s_seg, p->seg_cam,
                                                  p->seg_pose, p->camtab, p->posetab, points_ptr(p), p->U, p->gc, p->cost,
                                                  p->V, p->gp, p->W);
         PCS_CUDA(cudaGetLastError());
+        if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_b, p->stream));
     }
     k_symmetrize_blocks<<<grid_for((int64_t)p->C * 225, 256), 256, 0, p->stream>>>(p->C, 15, p->U);
     k_symmetrize_blocks<<<grid_for((int64_t)p->M * 36, 256), 256, 0, p->stream>>>(p->M, 6, p->V);
@@ -550,6 +552,8 @@ int pcs_problem_destroy(pcs_problem* p)
     dev_free(p->resid); dev_free(p->jvals); dev_free(p->seg_cam); dev_free(p->seg_pose); dev_free(p->seg_start);
     dev_free(p->s_key); dev_free(p->s_seg); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense);
     if (p->h_pin) cudaFreeHost(p->h_pin);
+    if (p->ev_a) cudaEventDestroy(p->ev_a);
+    if (p->ev_b) cudaEventDestroy(p->ev_b);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return PCS_OK;
@@ -980,6 +984,29 @@ int pcs_device_buffers_get(pcs_problem* p, pcs_device_buffers* out)
     if (!p->resid) PCS_TRY(dev_alloc(&p->resid, 2 * p->N));
     out->params = p->params; out->U = p->U; out->gc = p->gc; out->V = p->V; out->gp = p->gp; out->W = p->W;
     out->cost = p->cost; out->residual = p->resid; out->stream = (void*)p->stream;
+    return PCS_OK;
+}
+
+int pcs_timing_enable(pcs_problem* p, int on)
+{
+    PCS_REQUIRE(p, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    if (on && !p->ev_a) {
+        PCS_CUDA(cudaEventCreate(&p->ev_a));
+        PCS_CUDA(cudaEventCreate(&p->ev_b));
+    }
+    p->timing = on != 0;
+    return PCS_OK;
+}
+
+int pcs_timing_get(pcs_problem* p, double* ms)
+{
+    PCS_REQUIRE(p && ms && p->ev_a, "timing was never enabled");
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_CUDA(cudaEventSynchronize(p->ev_b));
+    float f = 0.f;
+    PCS_CUDA(cudaEventElapsedTime(&f, p->ev_a, p->ev_b));
+    *ms = f;
     return PCS_OK;
 }
 

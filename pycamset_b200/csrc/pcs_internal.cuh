@@ -81,6 +81,10 @@ struct pcs_problem {
     void* allreduce_user = nullptr;
     int rank = 0, world = 1;
 
+    // optional event timing of the normal-equation kernel
+    bool timing = false;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
     // LM workspace (pcs_solver.cu)
     void* lm_ws = nullptr;
 };

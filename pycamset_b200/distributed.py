@@ -1,0 +1,98 @@
+"""Multi-GPU plumbing: shard observations by target pose, combine camera blocks with NCCL.
+
+One process per GPU.  Pose blocks V_m, pose-camera blocks W_{c,m} and g_m live on exactly one rank; the camera
+blocks (and, inside the LM solver, the Schur-reduced camera system) are partial sums that are all-reduced over
+NVLink once per evaluation.  x is replicated; no observation ever moves.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def even_pose_ranges(n_poses: int, world: int):
+    """Contiguous pose ranges of (almost) equal size: [(start, stop)] * world."""
+    base, rem = divmod(n_poses, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def balanced_pose_ranges(obs_per_pose, world: int):
+    """Contiguous pose ranges balanced by observation count (greedy split of the prefix sum)."""
+    obs_per_pose = np.asarray(obs_per_pose, np.int64)
+    M = obs_per_pose.shape[0]
+    csum = np.concatenate([[0], np.cumsum(obs_per_pose)])
+    total = csum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        c = int(np.searchsorted(csum, target, side="left"))
+        c = min(max(c, cuts[-1]), M)
+        cuts.append(c)
+    cuts.append(M)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def shard_observations(cam, pose, key, uv, pose_range):
+    """Rows whose pose lies in [start, stop), with pose indices made local to the shard."""
+    s, e = pose_range
+    sel = (pose >= s) & (pose < e)
+    return cam[sel], pose[sel] - s, key[sel], uv[sel]
+
+
+def shard_param_string(params, n_cams, n_poses, pose_range, n_keys=0):
+    """Parameter string of a shard: all cameras, the shard's poses (and all points)."""
+    s, e = pose_range
+    params = np.asarray(params)
+    C15 = 15 * n_cams
+    parts = [params[:C15], params[C15 + 6 * s:C15 + 6 * e]]
+    if n_keys:
+        parts.append(params[C15 + 6 * n_poses:])
+    return np.concatenate(parts)
+
+
+class _DevicePtr:
+    """Zero-copy view of a raw device pointer through the CUDA array interface."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def tensor_from_ptr(ptr: int, n: int, device: int):
+    import torch
+    return torch.as_tensor(_DevicePtr(ptr, n), device=f"cuda:{device}")
+
+
+def install_nccl_allreduce(problem, group=None):
+    """Install a torch.distributed all-reduce as the LM solver's combine hook (op 0 = sum, 1 = max)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = problem.device
+
+    def fn(ptr, n, op, stream):
+        t = tensor_from_ptr(ptr, n, dev)
+        ext = torch.cuda.ExternalStream(stream, device=dev) if stream else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(ext):
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM, group=group)
+
+    problem.set_allreduce(fn, rank, world)
+    return rank, world
+
+
+def allreduce_camera_blocks(problem, group=None):
+    """Sum [U | gc | cost] (contiguous head of the normal-equation buffer) across ranks, on the problem's stream."""
+    import torch
+    import torch.distributed as dist
+
+    b = problem.device_buffers()
+    n = problem.n_cams * 240 + 1
+    t = tensor_from_ptr(b.U, n, problem.device)
+    ext = torch.cuda.ExternalStream(b.stream, device=problem.device)
+    with torch.cuda.stream(ext):
+        dist.all_reduce(t, group=group)
+    return t

@@ -170,13 +170,22 @@ class BundleProblem:
         L.check(self._lib.pcs_segments(self._h, _ptr(sc), _ptr(sp), _ptr(sl)))
         return sc, sp, sl
 
-    def normal_equations(self, x=None, with_W=True):
-        """Fused residual + Jacobian + J^T J / J^T r blocks (template chain).  Returns dict of host arrays."""
+    def normal_equations(self, x=None, with_W=True, out=None):
+        """Fused residual + Jacobian + J^T J / J^T r blocks (template chain).  Returns dict of host arrays.
+        `out` may hold preallocated (e.g. pinned) arrays U, gc, V, gp, W, cost_buf to receive the copies."""
         xk, xp = self._x(x)
         C, M, S = self.n_cams, self.n_poses, self.n_segments
-        U = np.empty((C, 15, 15)); gc = np.empty((C, 15)); V = np.empty((M, 6, 6)); gp = np.empty((M, 6))
-        W = np.empty((S, 15, 6)) if with_W else None
-        cost = np.empty(1)
+        out = out or {}
+        U = out.get("U", None); gc = out.get("gc", None); V = out.get("V", None); gp = out.get("gp", None)
+        U = np.empty((C, 15, 15)) if U is None else U
+        gc = np.empty((C, 15)) if gc is None else gc
+        V = np.empty((M, 6, 6)) if V is None else V
+        gp = np.empty((M, 6)) if gp is None else gp
+        W = out.get("W", None)
+        if W is None and with_W:
+            W = np.empty((S, 15, 6))
+        cost = out.get("cost_buf", None)
+        cost = np.empty(1) if cost is None else cost
         L.check(self._lib.pcs_normal_equations(self._h, xp, _ptr(U), _ptr(gc), _ptr(V), _ptr(gp), _ptr(W), _ptr(cost)))
         return dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
 
@@ -202,6 +211,14 @@ class BundleProblem:
         b = L.DeviceBuffers()
         L.check(self._lib.pcs_device_buffers_get(self._h, ct.byref(b)))
         return b
+
+    def timing_enable(self, on=True):
+        L.check(self._lib.pcs_timing_enable(self._h, 1 if on else 0))
+
+    def timing_normal_kernel_ms(self) -> float:
+        ms = ct.c_double()
+        L.check(self._lib.pcs_timing_get(self._h, ct.byref(ms)))
+        return ms.value
 
     def set_allreduce(self, fn, rank, world_size):
         """fn(ptr:int, n:int, op:int, stream:int) -> None; installed as the multi-GPU combine hook of the LM solver."""
