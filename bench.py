@@ -46,50 +46,104 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md "clocks line").
+
+    NVML (the library nvidia-smi itself reads) is polled every few ms from a thread, because the timed region of
+    this bench is tens of ms and `nvidia-smi -lms` cannot sample that fast; if NVML is unavailable the sampler
+    falls back to an `nvidia-smi --query-gpu ... -lms 100` subprocess."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device = device
-        self.rows = []
-        self.proc = None
+    def __init__(self, device, period_s=0.004):
+        self.device, self.period = device, period_s
+        self.sm, self.power, self.reasons = [], [], set()
+        self.sm_max = None
+        self.proc = self.thread = self.nvml = None
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device])
+            except Exception:
+                pass
+        return self.device
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self._physical_index())], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+    def _poll_nvml(self):
+        n = self.nvml
+        names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+        bits = {}
+        for k, v in names.items():
+            b = getattr(n, v, None) or getattr(n, v.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            if b is not None:
+                bits[k] = b
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(r[1])); mx = float(r[2])
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[1])); self.sm_max = float(r[2]); self.power.append(float(r[3]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "sm_min_mhz": float(np.min(self.sm)) if self.sm else None,
+                "power_w_max": float(np.max(self.power)) if self.power else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def build_shard(args, rank, world, device):
@@ -192,8 +246,8 @@ def workload_config(args, sh, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ring32", choices=sorted(WORKLOADS))
     ap.add_argument("--poses", type=int, default=0, help="override the workload's pose count")
@@ -262,6 +316,7 @@ def main():
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         kern_ms = []
         barrier()
+        launches0 = prob.launch_count()
         t_wall = time.perf_counter()
         for k in range(args.steps):
             flush_buf.zero_()                 # L2 flush, outside the per-step event pair
@@ -271,6 +326,7 @@ def main():
             kern_ms.append(prob.timing_normal_kernel_ms())
         barrier()
         wall_s = time.perf_counter() - t_wall
+        gpu_launches = prob.launch_count() - launches0
         clocks = sampler.stop() if rank == 0 else None
         prob.timing_enable(False)
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
@@ -366,7 +422,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mobs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "call": "BundleProblem.normal_equations(x_host) -> U, gc, V, gp, W, cost on host"},
-            "gpu_launches": args.steps * 5, "clocks": clocks, "lm": lm,
+            "gpu_launches": gpu_launches, "clocks": clocks, "lm": lm,
             "setup_s": setup_s, "wall_s_timed_region": wall_s,
         }
         print(json.dumps(out), flush=True)

@@ -181,6 +181,11 @@ PCS_API int pcs_lm_solve(pcs_problem* p, const double* x0 /*[n_free]*/, const pc
 PCS_API int pcs_timing_enable(pcs_problem* p, int on);
 PCS_API int pcs_timing_get(pcs_problem* p, double* normal_kernel_ms);
 
+/* Number of kernels of this library launched so far for the residual / Jacobian / normal-equation evaluations of
+ * this problem (cuBLAS / cuSOLVER launches inside pcs_lm_solve are not counted).  bench.py reports the difference
+ * over its timed region as `gpu_launches`. */
+PCS_API int pcs_launch_count(const pcs_problem* p, int64_t* n_kernels);
+
 /* Library / device probe: returns the device's SM count, or a negative pcs_status. */
 PCS_API int pcs_device_sm_count(int device);
 PCS_API const char* pcs_version(void);

@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpcs_b200.so"
 SOURCES = ["pcs_core.cu", "pcs_normal.cu", "pcs_solver.cu"]
-HEADERS = ["pcs_math.cuh", "pcs_internal.cuh", "pcs_gram_tiles.cuh", "../../include/pcs_b200.h"]
+HEADERS = ["pcs_math.cuh", "pcs_internal.cuh", "../../include/pcs_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",

@@ -61,7 +61,7 @@ __global__ void k_scatter_x(int64_t n_free, const int32_t* __restrict__ free_idx
 // update instead of once per observation (the reference calls Rodrigues inside the per-observation loop,
 // function_block_implementations.py:150-182).
 __global__ void k_prepare_tables(int C, int M, const double* __restrict__ params, double* __restrict__ camtab,
-                                 double* __restrict__ posetab)
+                                 double* __restrict__ posetab, double* __restrict__ dRtab)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < C) {
@@ -69,23 +69,26 @@ __global__ void k_prepare_tables(int C, int M, const double* __restrict__ params
         const double* e = params + 9 * (int64_t)C + 6 * (int64_t)t;
         double* o = camtab + (int64_t)t * CAM_STRIDE;
         for (int k = 0; k < 9; ++k) o[CAM_Q + k] = q[k];
-        double r[3] = {e[0], e[1], e[2]}, R[9], dR[27];
+        double r[3] = {e[0], e[1], e[2]}, R[9], Jl[9];
         rodrigues(r, R);
-        rodrigues_jac(r, dR);
+        rodrigues_left_jacobian(r, Jl);
         for (int k = 0; k < 9; ++k) o[CAM_R + k] = R[k];
         for (int k = 0; k < 3; ++k) o[CAM_T + k] = e[3 + k];
-        for (int k = 0; k < 27; ++k) o[CAM_DR + k] = dR[k];
+        for (int k = 0; k < 9; ++k) o[CAM_JL + k] = Jl[k];
+        o[30] = o[31] = 0.0;
+        if (dRtab) rodrigues_jac(r, dRtab + 27 * (int64_t)t);
     } else if (t < C + M) {
         int m = t - C;
         const double* e = params + 15 * (int64_t)C + 6 * (int64_t)m;
         double* o = posetab + (int64_t)m * POSE_STRIDE;
-        double r[3] = {e[0], e[1], e[2]}, R[9], dR[27];
+        double r[3] = {e[0], e[1], e[2]}, R[9], Jl[9];
         rodrigues(r, R);
-        rodrigues_jac(r, dR);
+        rodrigues_left_jacobian(r, Jl);
         for (int k = 0; k < 9; ++k) o[POSE_R + k] = R[k];
         for (int k = 0; k < 3; ++k) o[POSE_T + k] = e[3 + k];
-        for (int k = 0; k < 27; ++k) o[POSE_DR + k] = dR[k];
-        o[39] = 0.0;
+        for (int k = 0; k < 9; ++k) o[POSE_JL + k] = Jl[k];
+        o[21] = o[22] = o[23] = 0.0;
+        if (dRtab) rodrigues_jac(r, dRtab + 27 * (int64_t)t);
     }
 }
 
@@ -93,14 +96,19 @@ int launch_scatter_x(pcs_problem* p, const double* x_dev)
 {
     if (p->n_free > 0) {
         k_scatter_x<<<grid_for(p->n_free, 256), 256, 0, p->stream>>>(p->n_free, p->free_idx, x_dev, p->params);
+        ++p->n_launches;
         PCS_CUDA(cudaGetLastError());
     }
     return PCS_OK;
 }
 
-int launch_prepare(pcs_problem* p)
+// with_dR: also refresh the OpenCV dR/dr tables [C + M][27] the explicit-Jacobian / dense paths read
+int launch_prepare(pcs_problem* p, bool with_dR)
 {
-    k_prepare_tables<<<grid_for(p->C + p->M, 128), 128, 0, p->stream>>>(p->C, p->M, p->params, p->camtab, p->posetab);
+    if (with_dR && !p->dRtab) PCS_TRY(dev_alloc(&p->dRtab, 27 * ((int64_t)p->C + p->M)));
+    k_prepare_tables<<<grid_for(p->C + p->M, 128), 128, 0, p->stream>>>(p->C, p->M, p->params, p->camtab, p->posetab,
+                                                                       with_dR ? p->dRtab : nullptr);
+    ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;
 }
@@ -134,6 +142,7 @@ int launch_residual(pcs_problem* p, double* r_dev)
     if (p->N == 0) return PCS_OK;
     k_residual<<<grid_for(p->N, 256), 256, 0, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv,
                                                           p->camtab, p->posetab, points_ptr(p), (double2*)r_dev);
+    ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;
 }
@@ -167,6 +176,7 @@ int launch_cost_only(pcs_problem* p, double* cost_dev)
     int grid = std::min<int64_t>(grid_for(p->N, 256), (int64_t)p->sm_count * 8);
     k_cost<<<grid, 256, 0, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab, p->posetab,
                                         points_ptr(p), cost_dev);
+    ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;
 }
@@ -181,8 +191,9 @@ template <int P>
 __global__ void __launch_bounds__(128)
 k_jacobian(int64_t N, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose, const int32_t* __restrict__ key,
            const double2* __restrict__ uv, const double* __restrict__ camtab, const double* __restrict__ posetab,
-           const double* __restrict__ pts, const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask,
-           const uint8_t* __restrict__ key_mask, const int64_t* __restrict__ row_prefix, double* __restrict__ vals)
+           const double* __restrict__ dRtab, const double* __restrict__ pts, const uint16_t* __restrict__ cam_mask,
+           const uint8_t* __restrict__ pose_mask, const uint8_t* __restrict__ key_mask, const int64_t* __restrict__ row_prefix,
+           int C, double* __restrict__ vals)
 {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -200,11 +211,12 @@ k_jacobian(int64_t N, const int32_t* __restrict__ cam, const int32_t* __restrict
         const double Xt[3] = {pt[0], pt[1], pt[2]};
         const double* ct = camtab + (int64_t)c * CAM_STRIDE;
         const double* ptab = posetab + (int64_t)m * POSE_STRIDE;
-        double res[2], Xw[3];
+        double res[2], Bc[6], Bm[6];
         ObsJac J;
-        eval_obs(ct, ptab, Xt, o.x, o.y, res, J, Xw);
+        eval_obs(ct, ptab, Xt, o.x, o.y, res, J);
+        reference_rotation_blocks(J, ptab, dRtab + 27 * (int64_t)c, dRtab + 27 * ((int64_t)C + m), Xt, Bc, Bm);
         double ju[P], jv[P];
-        expand_rows<P>(J, ptab + POSE_R, ju, jv);
+        expand_rows<P>(J, Bc, Bm, ptab, ju, jv);
         uint32_t mask = (uint32_t)cam_mask[c] | ((uint32_t)pose_mask[m] << 15);
         if (P == 24) mask |= (uint32_t)key_mask[k] << 21;
         const int n = __popc(mask);
@@ -258,121 +270,6 @@ __global__ void k_csr_structure(int64_t N, int P, int C, int M, const int32_t* _
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K_ne v1 (reference implementation on the device; superseded by the tiled kernel in pcs_normal.cu):
-// (camera, pose)-sorted observations; a warp stages the augmented rows J' = [J | r] of 32 observations
-// in shared memory, then every lane owns 8 of the 253 upper-triangle entries of J'^T J' and walks the
-// observations; entries are flushed with FP64 atomics when the segment / camera changes.
-// ------------------------------------------------------------------------------------------------
-constexpr int NE_COLS = 22;
-constexpr int NE_ENT = NE_COLS * (NE_COLS + 1) / 2;  // 253
-__constant__ uint8_t c_ent_a[256];
-__constant__ uint8_t c_ent_b[256];
-
-__device__ __forceinline__ void ne_flush_entry(double v, int a, int b, int c, int m, int64_t seg, double* U, double* gc,
-                                               double* cost, double* V, double* gp, double* W)
-{
-    if (v == 0.0) return;
-    if (a < 15) {
-        if (b < 15) atomicAdd(U + (int64_t)c * 225 + a * 15 + b, v);
-        else if (b < 21) atomicAdd(W + seg * 90 + a * 6 + (b - 15), v);
-        else atomicAdd(gc + (int64_t)c * 15 + a, v);
-    } else if (a < 21) {
-        if (b < 21) atomicAdd(V + (int64_t)m * 36 + (a - 15) * 6 + (b - 15), v);
-        else atomicAdd(gp + (int64_t)m * 6 + (a - 15), v);
-    } else {
-        atomicAdd(cost, v);
-    }
-}
-
-__global__ void __launch_bounds__(128)
-k_normal_v1(int64_t N, int64_t obs_per_warp, const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv,
-            const int32_t* __restrict__ s_seg, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose,
-            const double* __restrict__ camtab, const double* __restrict__ posetab, const double* __restrict__ pts,
-            double* U, double* gc, double* cost, double* V, double* gp, double* W)
-{
-    constexpr int LD = 2 * NE_COLS + 1;  // 45: odd stride -> spread banks
-    __shared__ double Jsm[4][32 * LD];
-    __shared__ int segsm[4][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* js = Jsm[warp];
-    int* ss = segsm[warp];
-    const int64_t wg = blockIdx.x * (int64_t)(blockDim.x >> 5) + warp;
-    const int64_t begin = wg * obs_per_warp;
-    const int64_t end = min(N, begin + obs_per_warp);
-    if (begin >= N) return;
-
-    int ea[8], eb[8];
-    double acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int e = lane + 32 * j;
-        ea[j] = e < NE_ENT ? c_ent_a[e] : 0;
-        eb[j] = e < NE_ENT ? c_ent_b[e] : 0;
-        acc[j] = 0.0;
-    }
-    int64_t cur_seg = -1;
-    int cur_c = -1, cur_m = -1;
-
-    for (int64_t base = begin; base < end; base += 32) {
-        const int64_t i = base + lane;
-        int seg = -1;
-        double* row = js + lane * LD;
-        if (i < end) {
-            seg = s_seg[i];
-            const int c = seg_cam[seg], m = seg_pose[seg];
-            const int k = s_key[i];
-            const double2 o = s_uv[i];
-            const double* pt = pts + 3 * (int64_t)k;
-            const double Xt[3] = {pt[0], pt[1], pt[2]};
-            const double* ptab = posetab + (int64_t)m * POSE_STRIDE;
-            double res[2], Xw[3];
-            ObsJac J;
-            eval_obs(camtab + (int64_t)c * CAM_STRIDE, ptab, Xt, o.x, o.y, res, J, Xw);
-            double ju[21], jv[21];
-            expand_rows<21>(J, ptab, ju, jv);
-#pragma unroll
-            for (int col = 0; col < 21; ++col) {
-                row[col] = ju[col];
-                row[NE_COLS + col] = jv[col];
-            }
-            row[21] = res[0];
-            row[NE_COLS + 21] = res[1];
-        }
-        ss[lane] = seg;
-        __syncwarp();
-        const int cnt = (int)min((int64_t)32, end - base);
-        for (int o = 0; o < cnt; ++o) {
-            const int so = ss[o];
-            if (so != cur_seg) {
-                const int nc = seg_cam[so], nm = seg_pose[so];
-                if (cur_seg >= 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const bool cam_class = (ea[j] < 15 && (eb[j] < 15 || eb[j] == 21)) || ea[j] == 21;
-                        if (!cam_class || nc != cur_c) {
-                            if (lane + 32 * j < NE_ENT)
-                                ne_flush_entry(acc[j], ea[j], eb[j], cur_c, cur_m, cur_seg, U, gc, cost, V, gp, W);
-                            acc[j] = 0.0;
-                        }
-                    }
-                }
-                cur_seg = so; cur_c = nc; cur_m = nm;
-            }
-            const double* r = js + o * LD;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                acc[j] = fma(r[ea[j]], r[eb[j]], fma(r[NE_COLS + ea[j]], r[NE_COLS + eb[j]], acc[j]));
-        }
-        __syncwarp();
-    }
-    if (cur_seg >= 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (lane + 32 * j < NE_ENT) ne_flush_entry(acc[j], ea[j], eb[j], cur_c, cur_m, cur_seg, U, gc, cost, V, gp, W);
-    }
-}
-
 // mirror the upper triangles of U (15x15) and V (6x6) into the lower ones
 __global__ void k_symmetrize_blocks(int64_t n_blocks, int dim, double* __restrict__ blocks)
 {
@@ -384,28 +281,6 @@ __global__ void k_symmetrize_blocks(int64_t n_blocks, int dim, double* __restric
     if (a > b) blocks[blk * per + e] = blocks[blk * per + b * dim + a];
 }
 
-int launch_normal_blocks_v1(pcs_problem* p)
-{
-    PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)p->ne_doubles * sizeof(double), p->stream));
-    if (p->N > 0) {
-        // ~8 warps' worth of work per SM-resident warp slot; each warp walks a contiguous range
-        int64_t warps = std::max<int64_t>(1, std::min<int64_t>((p->N + 255) / 256, (int64_t)p->sm_count * 64));
-        int64_t per = ((p->N + warps - 1) / warps + 31) / 32 * 32;
-        warps = (p->N + per - 1) / per;
-        int grid = (int)((warps + 3) / 4);
-        if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a, p->stream));
-        k_normal_v1<<<grid, 128, 0, p->stream>>>(p->N, per, p->s_key, (const double2*)p->s_uv, p->s_seg, p->seg_cam,
-                                                 p->seg_pose, p->camtab, p->posetab, points_ptr(p), p->U, p->gc, p->cost,
-                                                 p->V, p->gp, p->W);
-        PCS_CUDA(cudaGetLastError());
-        if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_b, p->stream));
-    }
-    k_symmetrize_blocks<<<grid_for((int64_t)p->C * 225, 256), 256, 0, p->stream>>>(p->C, 15, p->U);
-    k_symmetrize_blocks<<<grid_for((int64_t)p->M * 36, 256), 256, 0, p->stream>>>(p->M, 6, p->V);
-    PCS_CUDA(cudaGetLastError());
-    return PCS_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Dense normal equations over the free parameters (both chains; small problems)
 // ------------------------------------------------------------------------------------------------
@@ -413,8 +288,8 @@ template <int P>
 __global__ void __launch_bounds__(128)
 k_normal_dense(int64_t N, int C, int M, int64_t n_free, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose,
                const int32_t* __restrict__ key, const double2* __restrict__ uv, const double* __restrict__ camtab,
-               const double* __restrict__ posetab, const double* __restrict__ pts, const int32_t* __restrict__ free_map,
-               double* JtJ, double* Jtr, double* cost)
+               const double* __restrict__ posetab, const double* __restrict__ dRtab, const double* __restrict__ pts,
+               const int32_t* __restrict__ free_map, double* JtJ, double* Jtr, double* cost)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -423,11 +298,13 @@ k_normal_dense(int64_t N, int C, int M, int64_t n_free, const int32_t* __restric
     const double* pt = pts + 3 * k;
     const double Xt[3] = {pt[0], pt[1], pt[2]};
     const double* ptab = posetab + m * POSE_STRIDE;
-    double res[2], Xw[3];
+    const double* ct = camtab + c * CAM_STRIDE;
+    double res[2], Bc[6], Bm[6];
     ObsJac J;
-    eval_obs(camtab + c * CAM_STRIDE, ptab, Xt, o.x, o.y, res, J, Xw);
+    eval_obs(ct, ptab, Xt, o.x, o.y, res, J);
+    reference_rotation_blocks(J, ptab, dRtab + 27 * c, dRtab + 27 * ((int64_t)C + m), Xt, Bc, Bm);
     double ju[P], jv[P];
-    expand_rows<P>(J, ptab + POSE_R, ju, jv);
+    expand_rows<P>(J, Bc, Bm, ptab, ju, jv);
     int32_t f[P];
 #pragma unroll
     for (int col = 0; col < P; ++col) {
@@ -490,22 +367,25 @@ __global__ void k_segment_flags(int64_t N, const uint64_t* __restrict__ keys, in
     if (i < N) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
-// s_seg holds the inclusive scan of flags on entry (segment id + 1)
+// seg_scan = inclusive scan of the segment-head flags (segment id + 1); writes the (camera, pose)-sorted SoA
 __global__ void k_segment_fill(int64_t N, int M, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
                                const int32_t* __restrict__ key_in, const double2* __restrict__ uv_in,
-                               int32_t* __restrict__ s_seg, int32_t* __restrict__ s_key, double2* __restrict__ s_uv,
-                               int32_t* __restrict__ seg_cam, int32_t* __restrict__ seg_pose, int64_t* __restrict__ seg_start)
+                               const int32_t* __restrict__ seg_scan, int32_t* __restrict__ s_cam, int32_t* __restrict__ s_pose,
+                               int32_t* __restrict__ s_key, double2* __restrict__ s_uv, int32_t* __restrict__ seg_cam,
+                               int32_t* __restrict__ seg_pose, int64_t* __restrict__ seg_start)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const int32_t seg = s_seg[i] - 1;
-    s_seg[i] = seg;
+    const int32_t seg = seg_scan[i] - 1;
     const uint32_t src = perm[i];
+    const int32_t c = (int32_t)(keys[i] / (uint64_t)M), m = (int32_t)(keys[i] % (uint64_t)M);
+    s_cam[i] = c;
+    s_pose[i] = m;
     s_key[i] = key_in[src];
     s_uv[i] = uv_in[src];
     if (i == 0 || keys[i] != keys[i - 1]) {
-        seg_cam[seg] = (int32_t)(keys[i] / (uint64_t)M);
-        seg_pose[seg] = (int32_t)(keys[i] % (uint64_t)M);
+        seg_cam[seg] = c;
+        seg_pose[seg] = m;
         seg_start[seg] = i;
     }
     if (i == N - 1) seg_start[seg + 1] = N;
@@ -550,7 +430,7 @@ int pcs_problem_destroy(pcs_problem* p)
     dev_free(p->free_map); dev_free(p->free_idx); dev_free(p->cam_mask); dev_free(p->pose_mask); dev_free(p->key_mask);
     dev_free(p->row_prefix); dev_free(p->params); dev_free(p->x); dev_free(p->camtab); dev_free(p->posetab);
     dev_free(p->resid); dev_free(p->jvals); dev_free(p->seg_cam); dev_free(p->seg_pose); dev_free(p->seg_start);
-    dev_free(p->s_key); dev_free(p->s_seg); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense);
+    dev_free(p->s_key); dev_free(p->s_cam); dev_free(p->s_pose); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense); dev_free(p->warp_seg); dev_free(p->dRtab);
     if (p->h_pin) cudaFreeHost(p->h_pin);
     if (p->ev_a) cudaEventDestroy(p->ev_a);
     if (p->ev_b) cudaEventDestroy(p->ev_b);
@@ -639,11 +519,11 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     uint64_t *keys_a = nullptr, *keys_b = nullptr;
     uint32_t *idx_a = nullptr, *idx_b = nullptr;
     int* bad = nullptr;
-    int32_t* flags = nullptr;
+    int32_t *flags = nullptr, *seg_scan = nullptr;
     void* tmp = nullptr;
     int rc = PCS_OK;
     auto cleanup = [&]() {
-        dev_free(keys_a); dev_free(keys_b); dev_free(idx_a); dev_free(idx_b); dev_free(bad); dev_free(flags);
+        dev_free(keys_a); dev_free(keys_b); dev_free(idx_a); dev_free(idx_b); dev_free(bad); dev_free(flags); dev_free(seg_scan);
         if (tmp) cudaFree(tmp);
     };
 #define BUILD_TRY(expr) do { rc = (expr); if (rc != PCS_OK) { cleanup(); return rc; } } while (0)
@@ -680,7 +560,8 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     BUILD_CUDA(cudaMemcpyAsync(&h_total, p->row_prefix + N, 8, cudaMemcpyDeviceToHost, st));
 
     // --- (camera, pose)-sorted layout -------------------------------------------------------------
-    BUILD_TRY(dev_alloc(&p->s_key, N)); BUILD_TRY(dev_alloc(&p->s_seg, N)); BUILD_TRY(dev_alloc(&p->s_uv, 2 * N));
+    BUILD_TRY(dev_alloc(&p->s_key, N)); BUILD_TRY(dev_alloc(&p->s_cam, N)); BUILD_TRY(dev_alloc(&p->s_pose, N));
+    BUILD_TRY(dev_alloc(&p->s_uv, 2 * N)); BUILD_TRY(dev_alloc(&seg_scan, N));
     int64_t n_seg = 0;
     if (N > 0) {
         PCS_REQUIRE(N < ((int64_t)1 << 31), "n_obs must be below 2^31 per problem (shard by pose across GPUs)");
@@ -688,9 +569,9 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
         BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, keys_a, keys_b, idx_a, idx_b, N, 0, key_bits, st));
         k_segment_flags<<<grid_for(N, 256), 256, 0, st>>>(N, keys_b, flags);
         need = tmp_bytes;
-        BUILD_CUDA(cub::DeviceScan::InclusiveSum(tmp, need, flags, p->s_seg, N, st));
+        BUILD_CUDA(cub::DeviceScan::InclusiveSum(tmp, need, flags, seg_scan, N, st));
         int32_t h_nseg = 0;
-        BUILD_CUDA(cudaMemcpyAsync(&h_nseg, p->s_seg + (N - 1), 4, cudaMemcpyDeviceToHost, st));
+        BUILD_CUDA(cudaMemcpyAsync(&h_nseg, seg_scan + (N - 1), 4, cudaMemcpyDeviceToHost, st));
         BUILD_CUDA(cudaStreamSynchronize(st));
         n_seg = h_nseg;
     } else {
@@ -700,8 +581,9 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     p->n_seg = n_seg;
     BUILD_TRY(dev_alloc(&p->seg_cam, n_seg)); BUILD_TRY(dev_alloc(&p->seg_pose, n_seg)); BUILD_TRY(dev_alloc(&p->seg_start, n_seg + 1));
     if (N > 0) {
-        k_segment_fill<<<grid_for(N, 256), 256, 0, st>>>(N, p->M, keys_b, idx_b, p->key, (const double2*)p->uv, p->s_seg,
-                                                         p->s_key, (double2*)p->s_uv, p->seg_cam, p->seg_pose, p->seg_start);
+        k_segment_fill<<<grid_for(N, 256), 256, 0, st>>>(N, p->M, keys_b, idx_b, p->key, (const double2*)p->uv, seg_scan, p->s_cam,
+                                                         p->s_pose, p->s_key, (double2*)p->s_uv, p->seg_cam, p->seg_pose,
+                                                         p->seg_start);
         BUILD_CUDA(cudaGetLastError());
     } else {
         BUILD_CUDA(cudaMemsetAsync(p->seg_start, 0, 8, st));
@@ -714,13 +596,6 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     BUILD_TRY(dev_alloc(&p->ne, p->ne_doubles));
     p->U = p->ne; p->gc = p->U + nU; p->cost = p->gc + ngc; p->V = p->ne + head; p->gp = p->V + nV; p->W = p->gp + ngp;
 
-    // entry table of the v1 normal-equation kernel
-    uint8_t ha[256] = {0}, hb[256] = {0};
-    int e = 0;
-    for (int a = 0; a < NE_COLS; ++a)
-        for (int b = a; b < NE_COLS; ++b) { ha[e] = (uint8_t)a; hb[e] = (uint8_t)b; ++e; }
-    BUILD_CUDA(cudaMemcpyToSymbolAsync(c_ent_a, ha, 256, 0, cudaMemcpyHostToDevice, st));
-    BUILD_CUDA(cudaMemcpyToSymbolAsync(c_ent_b, hb, 256, 0, cudaMemcpyHostToDevice, st));
     BUILD_CUDA(cudaStreamSynchronize(st));
     cleanup();
 #undef BUILD_TRY
@@ -852,14 +727,14 @@ int pcs_jacobian_values_dev(pcs_problem* p, const double* x_dev, double* vals_de
     PCS_REQUIRE(p && vals_dev, "NULL argument");
     PCS_CUDA(cudaSetDevice(p->device));
     if (x_dev) PCS_TRY(launch_scatter_x(p, x_dev));
-    PCS_TRY(launch_prepare(p));
+    PCS_TRY(launch_prepare(p, true));
     if (p->N == 0) return PCS_OK;
     const int grid = grid_for(p->N, 128);
     const size_t smem = (size_t)4 * 64 * p->P * sizeof(double);
     if (p->P == 21) {
         k_jacobian<21><<<grid, 128, smem, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab,
-                                                      p->posetab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
-                                                      p->row_prefix, vals_dev);
+                                                      p->posetab, p->dRtab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
+                                                      p->row_prefix, p->C, vals_dev);
     } else {
         static bool attr_set = false;
         if (!attr_set) {
@@ -867,10 +742,11 @@ int pcs_jacobian_values_dev(pcs_problem* p, const double* x_dev, double* vals_de
             attr_set = true;
         }
         k_jacobian<24><<<grid, 128, smem, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab,
-                                                      p->posetab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
-                                                      p->row_prefix, vals_dev);
+                                                      p->posetab, p->dRtab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
+                                                      p->row_prefix, p->C, vals_dev);
     }
     PCS_CUDA(cudaGetLastError());
+    ++p->n_launches;
     return PCS_OK;
 }
 
@@ -941,18 +817,18 @@ int pcs_normal_dense_dev_internal(pcs_problem* p)
     const int64_t n = p->n_free;
     PCS_REQUIRE(n > 0 && n <= 32768, "dense normal equations need 0 < n_free <= 32768");
     if (!p->dense) PCS_TRY(dev_alloc(&p->dense, n * n + n + 1));
-    PCS_TRY(launch_prepare(p));
+    PCS_TRY(launch_prepare(p, true));
     cudaStream_t st = p->stream;
     PCS_CUDA(cudaMemsetAsync(p->dense, 0, (size_t)(n * n + n + 1) * 8, st));
     double *dJ = p->dense, *dg = p->dense + n * n, *dc = dg + n;
     if (p->N) {
         if (p->P == 21)
             k_normal_dense<21><<<grid_for(p->N, 128), 128, 0, st>>>(p->N, p->C, p->M, n, p->cam, p->pose, p->key,
-                                                                    (const double2*)p->uv, p->camtab, p->posetab,
+                                                                    (const double2*)p->uv, p->camtab, p->posetab, p->dRtab,
                                                                     points_ptr(p), p->free_map, dJ, dg, dc);
         else
             k_normal_dense<24><<<grid_for(p->N, 128), 128, 0, st>>>(p->N, p->C, p->M, n, p->cam, p->pose, p->key,
-                                                                    (const double2*)p->uv, p->camtab, p->posetab,
+                                                                    (const double2*)p->uv, p->camtab, p->posetab, p->dRtab,
                                                                     points_ptr(p), p->free_map, dJ, dg, dc);
         PCS_CUDA(cudaGetLastError());
     }
@@ -984,6 +860,13 @@ int pcs_device_buffers_get(pcs_problem* p, pcs_device_buffers* out)
     if (!p->resid) PCS_TRY(dev_alloc(&p->resid, 2 * p->N));
     out->params = p->params; out->U = p->U; out->gc = p->gc; out->V = p->V; out->gp = p->gp; out->W = p->W;
     out->cost = p->cost; out->residual = p->resid; out->stream = (void*)p->stream;
+    return PCS_OK;
+}
+
+int pcs_launch_count(const pcs_problem* p, int64_t* n_kernels)
+{
+    PCS_REQUIRE(p && n_kernels, "NULL argument");
+    *n_kernels = p->n_launches;
     return PCS_OK;
 }
 
@@ -1023,8 +906,3 @@ int pcs_set_allreduce(pcs_problem* p, pcs_allreduce_fn fn, void* user, int rank,
 
 }  // extern "C"
 
-namespace pcs {
-// v1 is the default until the tiled kernel lands
-__attribute__((weak)) int launch_normal_blocks(pcs_problem* p) { return launch_normal_blocks_v1(p); }
-__attribute__((weak)) void lm_free(pcs_problem*) {}
-}  // namespace pcs

@@ -58,14 +58,15 @@ struct pcs_problem {
     // dynamic
     double* params = nullptr;      // [L]
     double* x = nullptr;           // [n_free]
-    double* camtab = nullptr;      // [C][48]
-    double* posetab = nullptr;     // [M][40]
+    double* camtab = nullptr;      // [C][32]
+    double* posetab = nullptr;     // [M][24]
+    double* dRtab = nullptr;       // [C + M][27] OpenCV dR/dr tables (explicit-Jacobian / dense paths; allocated on first use)
     double* resid = nullptr;       // [2N] (allocated on first use)
     double* jvals = nullptr;       // [nnz] (allocated on first use)
     // (camera, pose)-sorted layout for the normal equations
     int32_t *seg_cam = nullptr, *seg_pose = nullptr;  // [S]
     int64_t* seg_start = nullptr;                      // [S+1] into the sorted observation arrays
-    int32_t *s_key = nullptr, *s_seg = nullptr;        // [N] sorted
+    int32_t *s_key = nullptr, *s_cam = nullptr, *s_pose = nullptr;  // [N] sorted
     double* s_uv = nullptr;                            // [N][2] sorted
     // normal-equation outputs: one allocation [U | gc | cost | pad | V | gp | W]
     double* ne = nullptr;
@@ -85,6 +86,10 @@ struct pcs_problem {
     bool timing = false;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 
+    int64_t* warp_seg = nullptr;  // [ne_warps + 1] segment range of every warp of the normal-equation kernel
+    int64_t ne_warps = 0;
+    int64_t n_launches = 0;  // kernels launched by this library on behalf of the problem (pcs_launch_count)
+
     // LM workspace (pcs_solver.cu)
     void* lm_ws = nullptr;
 };
@@ -92,7 +97,7 @@ struct pcs_problem {
 namespace pcs {
 // kernels / launchers implemented in pcs_core.cu, used by pcs_solver.cu
 int launch_scatter_x(pcs_problem* p, const double* x_dev);
-int launch_prepare(pcs_problem* p);
+int launch_prepare(pcs_problem* p, bool with_dR = false);
 int launch_residual(pcs_problem* p, double* r_dev);
 int launch_cost_only(pcs_problem* p, double* cost_dev);
 int launch_normal_blocks(pcs_problem* p);

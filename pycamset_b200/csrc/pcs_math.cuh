@@ -7,19 +7,26 @@
 //   numba_flat_rodrigues_INPLACE / numba_rodrigues_jac  compiled_helpers.py:197-286
 //   chain product (matflow)  matmul_map.py:147-243:  J = [A | Pm [D_c | I] | Pm R_c [D_m | I] (| Pm R_c R_m)]
 //
-// Not a translation: rotations and their derivatives are hoisted out of the per-observation path
-// into per-camera / per-pose tables (the reference recomputes sin/cos for every observation), and
-// the projection Jacobian is evaluated in normalised coordinates instead of the reference's
-// z**7 / z**8 polynomial form (same function, better conditioned).
+// Not a translation:
+//   * rotations are hoisted out of the per-observation path into per-camera / per-pose tables (the reference
+//     recomputes sin/cos for every observation);
+//   * the rotation derivative uses the SO(3) left Jacobian instead of the 27-entry dR/dr table:
+//         d(R(r) X)/dr = -[R X]x Jl(r),      Jl = I + (1 - cos t)/t^2 [r]x + (t - sin t)/t^3 [r]x^2
+//     which is the same analytic derivative as the OpenCV formula the reference evaluates
+//     (compiled_helpers.py:237-286), needs 9 table entries instead of 27 and turns L * D(X) into
+//     (R X  x  L_row)^T Jl.  The normal-equation kernel goes one step further and accumulates J^T J in the
+//     tangent parametrisation (rows (R X x L_row)^T), applying Jl once per block afterwards;
+//   * the projection Jacobian is evaluated in normalised coordinates instead of the reference's
+//     z**7 / z**8 polynomial form (same function, better conditioned).
 #pragma once
 #include <cuda_runtime.h>
 
 namespace pcs {
 
-// Per-camera table row: [q(9) | R(9) | t(3) | dR(27)] = 48 doubles.
-constexpr int CAM_Q = 0, CAM_R = 9, CAM_T = 18, CAM_DR = 21, CAM_STRIDE = 48;
-// Per-pose table row: [R(9) | t(3) | dR(27) | pad] = 40 doubles.
-constexpr int POSE_R = 0, POSE_T = 9, POSE_DR = 12, POSE_STRIDE = 40;
+// Per-camera table row: [q(9) | R(9) | t(3) | Jl(9) | pad(2)] = 32 doubles.
+constexpr int CAM_Q = 0, CAM_R = 9, CAM_T = 18, CAM_JL = 21, CAM_STRIDE = 32;
+// Per-pose table row: [R(9) | t(3) | Jl(9) | pad(3)] = 24 doubles.
+constexpr int POSE_R = 0, POSE_T = 9, POSE_JL = 12, POSE_STRIDE = 24;
 
 __device__ __forceinline__ void rodrigues(const double r[3], double R[9])
 {
@@ -83,6 +90,34 @@ __device__ __forceinline__ void rodrigues_jac(const double r[3], double out[27])
     }
 }
 
+// Left Jacobian of SO(3), row-major 3x3:  d(R(r) X)/dr_i = Jl[:, i] x (R X).
+// theta < 1e-10 -> identity, matching the reference's switch to the so(3) generators (compiled_helpers.py:246-254).
+__device__ __forceinline__ void rodrigues_left_jacobian(const double r[3], double Jl[9])
+{
+    const double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    const double theta = sqrt(th2);
+    if (theta < 1e-10) {
+        Jl[0] = 1; Jl[1] = 0; Jl[2] = 0; Jl[3] = 0; Jl[4] = 1; Jl[5] = 0; Jl[6] = 0; Jl[7] = 0; Jl[8] = 1;
+        return;
+    }
+    double a, b;
+    if (theta < 0.05) {  // series: avoids the cancellation in 1 - cos and theta - sin
+        a = 0.5 - th2 * (1.0 / 24.0 - th2 * (1.0 / 720.0 - th2 * (1.0 / 40320.0)));
+        b = 1.0 / 6.0 - th2 * (1.0 / 120.0 - th2 * (1.0 / 5040.0 - th2 * (1.0 / 362880.0)));
+    } else {
+        double sh, ch, st, ct;
+        sincos(0.5 * theta, &sh, &ch);
+        sincos(theta, &st, &ct);
+        a = 2.0 * sh * sh / th2;
+        b = (theta - st) / (th2 * theta);
+    }
+    const double x = r[0], y = r[1], z = r[2];
+    // [r]x^2 = r r^T - |r|^2 I
+    Jl[0] = 1.0 + b * (x * x - th2); Jl[1] = -a * z + b * x * y;      Jl[2] = a * y + b * x * z;
+    Jl[3] = a * z + b * x * y;       Jl[4] = 1.0 + b * (y * y - th2); Jl[5] = -a * x + b * y * z;
+    Jl[6] = -a * y + b * x * z;      Jl[7] = a * x + b * y * z;       Jl[8] = 1.0 + b * (z * z - th2);
+}
+
 // Forward chain up to camera coordinates.
 struct ObsGeom {
     double Xt[3], Xw[3], Xc[3];
@@ -126,15 +161,17 @@ __device__ __forceinline__ Proj project(const double* __restrict__ q, const doub
 // Jacobian of one observation in "compressed" form:
 //   Au[5] / Av[5]: d u / d(k1,k2,p1,p2,k3), d v / d(k1,k2,p1,p2,k3)
 //   du/dfx = xD, du/dpx = 1, dv/dfy = yD, dv/dpy = 1, all other intrinsic entries are structural zeros
-//   Pm (2x3) = d(u,v)/dXc;  Bc (2x3) = Pm D_c;  N (2x3) = Pm R_c;  Bm (2x3) = N D_m
+//   Pm (2x3) = d(u,v)/dXc;  N (2x3) = Pm R_c
+//   Wc (2x3): rows (R_c X_w) x Pm_row   -- camera-rotation block in the tangent parametrisation; Bc = Wc Jl_c
+//   Wm (2x3): rows (R_m X_t) x N_row    -- pose-rotation block in the tangent parametrisation;   Bm = Wm Jl_m
 // Dense row layout (matflow column order): [fx px fy py k1 k2 p1 p2 k3 | Bc(3) Pm(3) | Bm(3) N(3) | (N R_m)(3)]
 struct ObsJac {
     double xD, yD;
     double Au[5], Av[5];
     double Pm[6];
-    double Bc[6];
+    double Wc[6];
     double N[6];
-    double Bm[6];
+    double Wm[6];
 };
 
 __device__ __forceinline__ void projection_jac(const double* __restrict__ q, const Proj& p, ObsJac& J)
@@ -177,6 +214,18 @@ __device__ __forceinline__ void left_times_drx(const double L[6], const double* 
     }
 }
 
+// out rows = Y x L_row  (L is 2x3): the derivative of L (R X) with respect to a left perturbation of R, Y = R X
+__device__ __forceinline__ void cross_rows(const double Y[3], const double L[6], double out[6])
+{
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const double* p = L + 3 * r;
+        out[3 * r + 0] = fma(Y[1], p[2], -(Y[2] * p[1]));
+        out[3 * r + 1] = fma(Y[2], p[0], -(Y[0] * p[2]));
+        out[3 * r + 2] = fma(Y[0], p[1], -(Y[1] * p[0]));
+    }
+}
+
 // out (2x3) = L (2x3) * R (3x3 row-major)
 __device__ __forceinline__ void left_times_R(const double L[6], const double* __restrict__ R, double out[6])
 {
@@ -187,22 +236,31 @@ __device__ __forceinline__ void left_times_R(const double L[6], const double* __
     }
 }
 
-// Full evaluation of one observation: residual + compressed Jacobian.
-__device__ __forceinline__ void eval_obs(const double* __restrict__ cam, const double* __restrict__ pose,
-                                         const double Xt[3], double u_obs, double v_obs, double res[2], ObsJac& J,
-                                         double Xw_out[3])
+// Y = R X (no translation)
+__device__ __forceinline__ void rotate(const double* __restrict__ R, const double X[3], double Y[3])
 {
-    double Xw[3], Xc[3];
-    transform(pose + POSE_R, pose + POSE_T, Xt, Xw);
-    transform(cam + CAM_R, cam + CAM_T, Xw, Xc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Y[a] = fma(R[3 * a], X[0], fma(R[3 * a + 1], X[1], R[3 * a + 2] * X[2]));
+}
+
+// Full evaluation of one observation: residual + compressed Jacobian (rotation blocks in tangent form).
+__device__ __forceinline__ void eval_obs(const double* __restrict__ cam, const double* __restrict__ pose,
+                                         const double Xt[3], double u_obs, double v_obs, double res[2], ObsJac& J)
+{
+    double Ym[3], Xw[3], Yc[3], Xc[3];
+    rotate(pose + POSE_R, Xt, Ym);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Xw[a] = Ym[a] + pose[POSE_T + a];
+    rotate(cam + CAM_R, Xw, Yc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Xc[a] = Yc[a] + cam[CAM_T + a];
     const Proj p = project(cam + CAM_Q, Xc);
     res[0] = p.u - u_obs;
     res[1] = p.v - v_obs;
     projection_jac(cam + CAM_Q, p, J);
-    left_times_drx(J.Pm, cam + CAM_DR, Xw, J.Bc);
+    cross_rows(Yc, J.Pm, J.Wc);
     left_times_R(J.Pm, cam + CAM_R, J.N);
-    left_times_drx(J.N, pose + POSE_DR, Xt, J.Bm);
-    Xw_out[0] = Xw[0]; Xw_out[1] = Xw[1]; Xw_out[2] = Xw[2];
+    cross_rows(Ym, J.N, J.Wm);
 }
 
 // Residual only.
@@ -217,10 +275,26 @@ __device__ __forceinline__ void eval_residual(const double* __restrict__ cam, co
     res[1] = p.v - v_obs;
 }
 
+// Rotation blocks exactly as the reference evaluates them: Bc = Pm D_c(X_w), Bm = N D_m(X_t) with
+// D[a][i] = sum_j dR[i][3a+j] X[j] from the OpenCV dR/dr table (function_block_implementations.py:157-182,
+// compiled_helpers.py:237-286).  Used by the explicit-Jacobian (jac_fn drop-in) and dense paths so that their
+// entries match the reference's to rounding; the OpenCV formula itself loses ~1e-8 relative accuracy for
+// |rvec| ~ 1e-5 (cancellation), which the left-Jacobian form used by the normal-equation kernel does not.
+__device__ __forceinline__ void reference_rotation_blocks(const ObsJac& J, const double* __restrict__ pose,
+                                                          const double* __restrict__ cam_dR, const double* __restrict__ pose_dR,
+                                                          const double Xt[3], double Bc[6], double Bm[6])
+{
+    double Xw[3];
+    transform(pose + POSE_R, pose + POSE_T, Xt, Xw);
+    left_times_drx(J.Pm, cam_dR, Xw, Bc);
+    left_times_drx(J.N, pose_dR, Xt, Bm);
+}
+
 // Expand the compressed Jacobian into dense matflow rows (P = 21, or 24 with the point block).
 // row 0 = d u / d(.), row 1 = d v / d(.)
 template <int P>
-__device__ __forceinline__ void expand_rows(const ObsJac& J, const double* __restrict__ Rm, double ju[P], double jv[P])
+__device__ __forceinline__ void expand_rows(const ObsJac& J, const double Bc[6], const double Bm[6],
+                                            const double* __restrict__ pose, double ju[P], double jv[P])
 {
     ju[0] = J.xD; ju[1] = 1.0; ju[2] = 0.0; ju[3] = 0.0;
     jv[0] = 0.0; jv[1] = 0.0; jv[2] = J.yD; jv[3] = 1.0;
@@ -228,14 +302,14 @@ __device__ __forceinline__ void expand_rows(const ObsJac& J, const double* __res
     for (int k = 0; k < 5; ++k) { ju[4 + k] = J.Au[k]; jv[4 + k] = J.Av[k]; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        ju[9 + k] = J.Bc[k];  jv[9 + k] = J.Bc[3 + k];
+        ju[9 + k] = Bc[k];    jv[9 + k] = Bc[3 + k];
         ju[12 + k] = J.Pm[k]; jv[12 + k] = J.Pm[3 + k];
-        ju[15 + k] = J.Bm[k]; jv[15 + k] = J.Bm[3 + k];
+        ju[15 + k] = Bm[k];   jv[15 + k] = Bm[3 + k];
         ju[18 + k] = J.N[k];  jv[18 + k] = J.N[3 + k];
     }
     if (P == 24) {
         double Bk[6];
-        left_times_R(J.N, Rm, Bk);
+        left_times_R(J.N, pose + POSE_R, Bk);
 #pragma unroll
         for (int k = 0; k < 3; ++k) { ju[21 + k] = Bk[k]; jv[21 + k] = Bk[3 + k]; }
     }

@@ -220,6 +220,11 @@ class BundleProblem:
         L.check(self._lib.pcs_timing_get(self._h, ct.byref(ms)))
         return ms.value
 
+    def launch_count(self) -> int:
+        n = ct.c_int64()
+        L.check(self._lib.pcs_launch_count(self._h, ct.byref(n)))
+        return n.value
+
     def set_allreduce(self, fn, rank, world_size):
         """fn(ptr:int, n:int, op:int, stream:int) -> None; installed as the multi-GPU combine hook of the LM solver."""
         def _cb(user, buf, n, op, stream):
