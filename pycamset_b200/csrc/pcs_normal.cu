@@ -118,7 +118,7 @@ __device__ __forceinline__ void flush_camera(NeAcc& A, int lane, int c, double* 
     }
 }
 
-template <int CTAS_PER_SM, int MODE>
+template <int CTAS_PER_SM>
 __global__ void __launch_bounds__(NE_WARPS * 32, CTAS_PER_SM)
 k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_pose,
          const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv, const int64_t* __restrict__ seg_start,
@@ -166,7 +166,7 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
             const int64_t i = base + 32 + lane;
             if (i < end) { c_n = s_cam[i]; m_n = s_pose[i]; k_n = s_key[i]; uv_n = s_uv[i]; }
         }
-        if (MODE != 2 && lane < cnt) {
+        if (lane < cnt) {
             const double* pt = pts + 3 * (int64_t)k;
             const double Xt[3] = {pt[0], pt[1], pt[2]};
             const double* ct = camtab + (int64_t)c * CAM_STRIDE;
@@ -206,7 +206,7 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
                 ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
             }
             const int k0 = a >> 1, k1 = (b - 1) >> 1;
-            for (int ks = k0; MODE != 1 && ks <= k1; ++ks) {
+            for (int ks = k0; ks <= k1; ++ks) {
                 const double* f = ws + 32 * ks + (ld_L ^ (((ks & 1) << 3) | (ks & 2)));
                 double v0 = f[0], v1 = f[NE_TILE_DOUBLES], v2 = f[2 * NE_TILE_DOUBLES];
                 if (ks == k0 || ks == k1) {  // boundary k-steps may hold rows of a neighbouring segment (or stale rows)
@@ -228,182 +228,6 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
         flush_segment(A, lane, cur_seg, cur_m, V, gp, W);
         flush_camera(A, lane, cur_c, U, gc);
         if (lane == 27) atomicAdd(cost, A.a00[0]);  // row 6, column 6 of tile (0,0) = r . r
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Warp-specialised variant: one CTA of 16 warps per SM.  Warps 0..3 ("Gram warps", one per SM sub-partition)
-// own one stream of whole segments each and do nothing but fragment loads + DMMA + flushes; warps 4..15
-// ("evaluation warps") evaluate batches of their stream round-robin (batch j -> evaluation warp j mod 3) into one
-// 12 KB staging buffer each.  full / empty mbarriers hand the buffers over, so the FP64 pipe always has DMMA work
-// queued while the latency-bound evaluation of the next batches is in flight.
-// ------------------------------------------------------------------------------------------------
-constexpr int WS_GRAM = 4, WS_EVAL_PER_GRAM = 3, WS_EVAL = WS_GRAM * WS_EVAL_PER_GRAM, WS_THREADS = 32 * (WS_GRAM + WS_EVAL);
-constexpr int WS_META_INTS = 80;  // per buffer: cam[32], pose[32], count, pad
-constexpr size_t WS_SMEM_BYTES = (size_t)WS_EVAL * NE_WARP_DOUBLES * 8 + (size_t)WS_EVAL * WS_META_INTS * 4 + 2 * WS_EVAL * 8;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-__global__ void __launch_bounds__(WS_THREADS, 1)
-k_normal_ws(int n_streams, const int64_t* __restrict__ stream_seg, const int32_t* __restrict__ s_cam,
-            const int32_t* __restrict__ s_pose, const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv,
-            const int64_t* __restrict__ seg_start, const double* __restrict__ camtab, const double* __restrict__ posetab,
-            const double* __restrict__ pts, double* __restrict__ U, double* __restrict__ gc, double* __restrict__ cost,
-            double* __restrict__ V, double* __restrict__ gp, double* __restrict__ W)
-{
-    extern __shared__ __align__(16) double ne_smem[];
-    int* const meta_all = reinterpret_cast<int*>(ne_smem + WS_EVAL * NE_WARP_DOUBLES);
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(meta_all + WS_EVAL * WS_META_INTS);  // full[12], empty[12]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * WS_EVAL; ++i) mbar_init(bars + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const bool is_gram = warp < WS_GRAM;
-    const int g = is_gram ? warp : (warp - WS_GRAM) % WS_GRAM;   // stream slot of this warp
-    const int q = is_gram ? 0 : (warp - WS_GRAM) / WS_GRAM;      // evaluation warp: batches j = q (mod 3)
-    const int stream = blockIdx.x * WS_GRAM + g;
-    if (stream >= n_streams) return;
-    const int64_t sb = stream_seg[stream], se = stream_seg[stream + 1];
-    if (sb >= se) return;
-    const int64_t begin = seg_start[sb], end = seg_start[se];
-    const int64_t n_batches = (end - begin + 31) >> 5;
-
-    if (!is_gram) {
-        // ---------------- evaluation warp ----------------
-        const int e = warp - WS_GRAM;  // buffer index: g + 4 q
-        double* const ws = ne_smem + e * NE_WARP_DOUBLES;
-        int* const meta = meta_all + e * WS_META_INTS;
-        uint64_t* const full = bars + e;
-        uint64_t* const empty = bars + WS_EVAL + e;
-        double* const st_u = ws + stage_row(lane, 0);
-        double* const st_v = ws + stage_row(lane, 1);
-        const int st_rot = stage_rot(lane);
-        int c_n = -1, m_n = -1, k_n = 0;
-        double2 uv_n = make_double2(0.0, 0.0);
-        {
-            const int64_t i = begin + 32 * (int64_t)q + lane;
-            if (i < end) { c_n = s_cam[i]; m_n = s_pose[i]; k_n = s_key[i]; uv_n = s_uv[i]; }
-        }
-        uint32_t round = 0;
-        for (int64_t j = q; j < n_batches; j += WS_EVAL_PER_GRAM, ++round) {
-            const int64_t base = begin + 32 * j;
-            const int cnt = (int)min((int64_t)32, end - base);
-            const int c = c_n, m = m_n, k = k_n;
-            const double2 o = uv_n;
-            {
-                const int64_t i = base + 32 * WS_EVAL_PER_GRAM + lane;
-                if (i < end) { c_n = s_cam[i]; m_n = s_pose[i]; k_n = s_key[i]; uv_n = s_uv[i]; }
-            }
-            double res[2] = {0.0, 0.0};
-            ObsJac J;
-            if (lane < cnt) {
-                const double* pt = pts + 3 * (int64_t)k;
-                const double Xt[3] = {pt[0], pt[1], pt[2]};
-                eval_obs(camtab + (int64_t)c * CAM_STRIDE, posetab + (int64_t)m * POSE_STRIDE, Xt, o.x, o.y, res, J);
-            }
-            if (round > 0) mbar_wait(empty, (round - 1) & 1);  // the Gram warp has released this buffer
-            if (lane < cnt) {
-                {
-                    const double t0[8] = {J.Wm[0], J.Wm[1], J.Wm[2], J.N[0], J.N[1], J.N[2], res[0], 0.0};
-                    const double t1[8] = {J.xD, 1.0, 0.0, 0.0, J.Au[0], J.Au[1], J.Au[2], J.Au[3]};
-                    const double t2[8] = {J.Au[4], J.Wc[0], J.Wc[1], J.Wc[2], J.Pm[0], J.Pm[1], J.Pm[2], 0.0};
-                    stage_store_row(st_u, st_rot, t0, t1, t2);
-                }
-                {
-                    const double t0[8] = {J.Wm[3], J.Wm[4], J.Wm[5], J.N[3], J.N[4], J.N[5], res[1], 0.0};
-                    const double t1[8] = {0.0, 0.0, J.yD, 1.0, J.Av[0], J.Av[1], J.Av[2], J.Av[3]};
-                    const double t2[8] = {J.Av[4], J.Wc[3], J.Wc[4], J.Wc[5], J.Pm[3], J.Pm[4], J.Pm[5], 0.0};
-                    stage_store_row(st_v, st_rot, t0, t1, t2);
-                }
-            }
-            meta[lane] = c;
-            meta[32 + lane] = m;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full);
-        }
-        return;
-    }
-
-    // ---------------- Gram warp ----------------
-    NeAcc A;
-    A.a00[0] = A.a00[1] = A.a01[0] = A.a01[1] = A.a02[0] = A.a02[1] = 0.0;
-    A.a11[0] = A.a11[1] = A.a12[0] = A.a12[1] = A.a22[0] = A.a22[1] = 0.0;
-    int64_t cur_seg = sb - 1;
-    int cur_c = -1, cur_m = -1, last_c = -1, last_m = -1;
-    const int g8 = lane >> 2, jb = (lane >> 1) & 1, jr = lane & 1;
-    const int ld_L = 16 * jb + 8 * jr + (g8 ^ (4 * jb));
-    for (int64_t j = 0; j < n_batches; ++j) {
-        const int slot = (int)(j % WS_EVAL_PER_GRAM);
-        const uint32_t round = (uint32_t)(j / WS_EVAL_PER_GRAM);
-        const int e = g + WS_GRAM * slot;
-        const double* const ws = ne_smem + e * NE_WARP_DOUBLES;
-        const int* const meta = meta_all + e * WS_META_INTS;
-        const int cnt = (int)min((int64_t)32, end - (begin + 32 * j));
-        mbar_wait(bars + e, round & 1);
-        const int c = meta[lane], m = meta[32 + lane];
-        int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
-        if (lane == 0) { pc = last_c; pm = last_m; }
-        const unsigned heads = __ballot_sync(0xffffffffu, lane < cnt && (c != pc || m != pm));
-        last_c = __shfl_sync(0xffffffffu, c, cnt - 1);
-        last_m = __shfl_sync(0xffffffffu, m, cnt - 1);
-        unsigned pieces = heads | 1u;
-        while (pieces) {
-            const int a = __ffs(pieces) - 1;
-            pieces &= pieces - 1;
-            const int b = pieces ? __ffs(pieces) - 1 : cnt;
-            if ((heads >> a) & 1u) {
-                if (cur_c >= 0) flush_segment(A, lane, cur_seg, cur_m, V, gp, W);
-                const int nc = __shfl_sync(0xffffffffu, c, a);
-                if (nc != cur_c && cur_c >= 0) flush_camera(A, lane, cur_c, U, gc);
-                ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
-            }
-            const int k0 = a >> 1, k1 = (b - 1) >> 1;
-            for (int ks = k0; ks <= k1; ++ks) {
-                const double* f = ws + 32 * ks + (ld_L ^ (((ks & 1) << 3) | (ks & 2)));
-                double v0 = f[0], v1 = f[NE_TILE_DOUBLES], v2 = f[2 * NE_TILE_DOUBLES];
-                if (ks == k0 || ks == k1) {
-                    const int ob = 2 * ks + jb;
-                    const bool ok = ob >= a && ob < b;
-                    v0 = ok ? v0 : 0.0; v1 = ok ? v1 : 0.0; v2 = ok ? v2 : 0.0;
-                }
-                dmma884(A.a00[0], A.a00[1], v0, v0);
-                dmma884(A.a01[0], A.a01[1], v0, v1);
-                dmma884(A.a02[0], A.a02[1], v0, v2);
-                dmma884(A.a11[0], A.a11[1], v1, v1);
-                dmma884(A.a12[0], A.a12[1], v1, v2);
-                dmma884(A.a22[0], A.a22[1], v2, v2);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + WS_EVAL + e);
-    }
-    if (cur_c >= 0) {
-        flush_segment(A, lane, cur_seg, cur_m, V, gp, W);
-        flush_camera(A, lane, cur_c, U, gc);
-        if (lane == 27) atomicAdd(cost, A.a00[0]);
     }
 }
 
@@ -545,42 +369,24 @@ int launch_normal_blocks(pcs_problem* p)
     const int64_t zero_doubles = (p->V - p->ne) + (int64_t)p->M * 42;
     PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
     if (p->N == 0) return PCS_OK;
-    static const int variant = [] { const char* e = std::getenv("PCS_NE_VARIANT"); return e ? e[0] - '0' : 0; }();
-    if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a, p->stream));
-    if (variant == 0) {
-        // warp-specialised: one CTA of 16 warps per SM, 4 streams per CTA
-        static bool attr_ws = false;
-        if (!attr_ws) {
-            PCS_CUDA(cudaFuncSetAttribute(k_normal_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
-            attr_ws = true;
-        }
-        int64_t n_streams = std::min<int64_t>((p->N + 95) / 96, (int64_t)p->sm_count * WS_GRAM);
-        n_streams = std::max<int64_t>(1, std::min<int64_t>(n_streams, p->n_seg));
-        PCS_TRY(ensure_ranges(p, n_streams));
-        const int grid = (int)((n_streams + WS_GRAM - 1) / WS_GRAM);
-        k_normal_ws<<<grid, WS_THREADS, WS_SMEM_BYTES, p->stream>>>((int)n_streams, p->warp_seg, p->s_cam, p->s_pose, p->s_key,
-                                                                  (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
-                                                                  p->tmpl, p->U, p->gc, p->cost, p->V, p->gp, p->W);
-    } else {
-        // every warp evaluates and accumulates its own batches; 4 x 128 registers (variant 1) or 3 x 154 (variant 3)
-        const int ctas = variant == 3 ? 3 : 4;
-        static const int mode = [] { const char* e = std::getenv("PCS_NE_MODE"); return e ? e[0] - '0' : 0; }();
-        auto kern = ctas == 3 ? (mode == 1 ? k_normal<3, 1> : mode == 2 ? k_normal<3, 2> : k_normal<3, 0>)
-                              : (mode == 1 ? k_normal<4, 1> : mode == 2 ? k_normal<4, 2> : k_normal<4, 0>);
-        static bool attr_set = false;
-        const size_t smem = (size_t)NE_WARPS * NE_WARP_DOUBLES * sizeof(double);
-        if (!attr_set) {
-            PCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
-        int64_t n_warps = std::min<int64_t>((p->N + 63) / 64, (int64_t)p->sm_count * ctas * NE_WARPS);
-        n_warps = std::max<int64_t>(1, std::min<int64_t>(n_warps, p->n_seg));
-        PCS_TRY(ensure_ranges(p, n_warps));
-        const int grid = (int)((n_warps + NE_WARPS - 1) / NE_WARPS);
-        kern<<<grid, NE_WARPS * 32, smem, p->stream>>>((int)n_warps, p->warp_seg, p->s_cam, p->s_pose, p->s_key,
-                                                      (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab, p->tmpl,
-                                                      p->U, p->gc, p->cost, p->V, p->gp, p->W);
+    // resident CTAs per SM: 4 x 128 registers (default) or 3 x 154; PCS_NE_CTAS=3 selects the latter for A/B runs
+    static const int ctas = [] { const char* e = std::getenv("PCS_NE_CTAS"); return e && e[0] == '3' ? 3 : 4; }();
+    auto kern = ctas == 3 ? k_normal<3> : k_normal<4>;
+    static bool attr_set = false;
+    const size_t smem = (size_t)NE_WARPS * NE_WARP_DOUBLES * sizeof(double);
+    if (!attr_set) {
+        PCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
     }
+    // persistent-style grid: `ctas` CTAs of NE_WARPS warps per SM; at least ~64 observations per warp
+    int64_t n_warps = std::min<int64_t>((p->N + 63) / 64, (int64_t)p->sm_count * ctas * NE_WARPS);
+    n_warps = std::max<int64_t>(1, std::min<int64_t>(n_warps, p->n_seg));
+    PCS_TRY(ensure_ranges(p, n_warps));
+    const int grid = (int)((n_warps + NE_WARPS - 1) / NE_WARPS);
+    if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a, p->stream));
+    kern<<<grid, NE_WARPS * 32, smem, p->stream>>>((int)n_warps, p->warp_seg, p->s_cam, p->s_pose, p->s_key,
+                                                  (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab, p->tmpl,
+                                                  p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
     const int pose_blocks = (p->M + 63) / 64;
     const int64_t w_blocks = (p->n_seg + 3) / 4;
