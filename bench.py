@@ -28,6 +28,11 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "Mobs/s residual+Jacobian+JtJ eval"
 ALGO_BYTES_PER_OBS = 28.0  # (u, v) 16 B + cam, pose, key 12 B; K_ne writes O(params), not O(N)
+# FP64 work of K_ne per observation: ~150 evaluation FMA-slots + 3 DMMA m8n8k4 (768 FMA slots issued,
+# ~420 of them structurally needed); 2 flop per FMA.
+FP64_ISSUED_FLOP_PER_OBS = 2.0 * (150 + 768)
+FP64_USEFUL_FLOP_PER_OBS = 2.0 * (150 + 420)
+FP64_PEAK_TFLOPS = 36.9    # measured on this pool's B200 by tools/fp64_peak.cu (profiles/r1_fp64_peak_b200.json)
 
 WORKLOADS = {
     # name: (layout, n_cams, poses, detect_prob, scaling)
@@ -418,7 +423,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "normal-equation kernel (K_ne)",
                          "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_obs": ALGO_BYTES_PER_OBS,
-                         "note": "FP64-ALU bound by design (SURVEY.md 7): see DESIGN.md for the FP64 roof"},
+                         "note": "K_ne is bound by the FP64 pipe, not HBM (DESIGN.md 4); see the fp64 object",
+                         "fp64": {"issued_tflops": FP64_ISSUED_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12,
+                                  "useful_tflops": FP64_USEFUL_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12,
+                                  "peak_tflops": FP64_PEAK_TFLOPS, "peak_source": "measured (tools/fp64_peak.cu)",
+                                  "frac_issued": FP64_ISSUED_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mobs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "call": "BundleProblem.normal_equations(x_host) -> U, gc, V, gp, W, cost on host"},
