@@ -263,6 +263,37 @@ __device__ __forceinline__ void eval_obs(const double* __restrict__ cam, const d
     cross_rows(Ym, J.N, J.Wm);
 }
 
+// Camera-side evaluation for the normal-equation kernel: residual, intrinsic entries, Pm and the camera-rotation
+// rows in tangent form.  The pose columns are NOT evaluated per observation: within one (camera, pose) segment they
+// are the extrinsic columns times a constant 6x6 adjoint (see pcs_normal.cu), so only their segment sums are formed.
+struct ObsJacCam {
+    double xD, yD;
+    double Au[5], Av[5];
+    double Pm[6];
+    double Wc[6];
+};
+
+__device__ __forceinline__ void eval_obs_cam(const double* __restrict__ cam, const double* __restrict__ pose,
+                                             const double Xt[3], double u_obs, double v_obs, double res[2], ObsJacCam& J)
+{
+    double Xw[3], Yc[3], Xc[3];
+    transform(pose + POSE_R, pose + POSE_T, Xt, Xw);
+    rotate(cam + CAM_R, Xw, Yc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Xc[a] = Yc[a] + cam[CAM_T + a];
+    const Proj p = project(cam + CAM_Q, Xc);
+    res[0] = p.u - u_obs;
+    res[1] = p.v - v_obs;
+    ObsJac full;
+    projection_jac(cam + CAM_Q, p, full);
+    J.xD = full.xD; J.yD = full.yD;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { J.Au[k] = full.Au[k]; J.Av[k] = full.Av[k]; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) J.Pm[k] = full.Pm[k];
+    cross_rows(Yc, J.Pm, J.Wc);
+}
+
 // Residual only.
 __device__ __forceinline__ void eval_residual(const double* __restrict__ cam, const double* __restrict__ pose,
                                               const double Xt[3], double u_obs, double v_obs, double res[2])

@@ -7,18 +7,23 @@
 // Design (B200, FP64):
 //   * Observations are sorted by (camera, pose) at problem build; a "segment" is one (camera, pose) pair.
 //   * A warp owns a contiguous range of WHOLE segments (balanced by observation count) and walks it in batches
-//     of 32 observations (inputs of batch n+1 are prefetched while batch n runs), one lane per observation: the lane evaluates residual and Jacobian in registers and
-//     parks its two augmented rows  J' = [pose(6) r 0 | cam(0..7) | cam(8..14) 0]  (24 doubles each) in shared
-//     memory -- 12 KB per warp, swizzled so that both the 16-byte row stores and the fragment loads below are
-//     bank-conflict free.
-//   * The Gram update  G += J'^T J'  runs on the FP64 tensor cores: per 2 observations (4 rows = one k-step) the warp
-//     loads 3 fragment values per lane and issues 6 DMMA m8n8k4 (the upper-triangular 8x8 tile pairs of the 24x24
-//     Gram matrix).  A-fragment and B-fragment of a tile are the same register, so a k-step costs 3 LDS.64.
-//   * Tiles (0,*) hold V_m, g_m, W_{c,m} (flushed per segment: W by plain stores -- the warp owns the segment --
-//     V/g_m by FP64 reductions) plus g_c and r.r in row 6, which keep accumulating; tiles (1,1) (1,2) (2,2) hold
-//     U_c and are flushed when the camera changes.
-//   * Rotation rows are accumulated in the tangent parametrisation ((R X) x row, pcs_math.cuh); k_normal_epilogue
-//     applies the SO(3) left Jacobians once per block (U_c, V_m, W_s, g) afterwards.
+//     of 32 observations (inputs of batch n+1 are prefetched while batch n runs), one lane per observation: the
+//     lane evaluates residual and Jacobian in registers and parks its two augmented rows
+//         J' = [cam(0..7) | cam(8..14) r]        (16 doubles each)
+//     in shared memory -- 8 KB per warp, swizzled so that both the 16-byte row stores and the fragment loads below
+//     are bank-conflict free.
+//   * Only the CAMERA columns are accumulated per observation.  Inside one segment the six pose columns are the
+//     six extrinsic columns times a constant adjoint,  [w_m | n] = [w_c | p] T,  T = [[R_c, 0], [[R_c t_m]x R_c, R_c]]
+//     (rows in the tangent parametrisation, pcs_math.cuh), so V_m, g_m and W_{c,m} follow from the SEGMENT's camera
+//     Gram matrix G_s at flush time:   W_s = G_s[:, 9:15] T,   V_m += T^T G_s[9:15, 9:15] T,   g_m += T^T g_s[9:15].
+//     That halves the per-observation Gram work: 16 columns = exactly two 8-column tiles.
+//   * The Gram update  G += J'^T J'  runs on the FP64 tensor path: per 2 observations (4 rows = one k-step) the warp
+//     loads 2 fragment values per lane and issues 3 DMMA m8n8k4 (tile pairs AA, AB, BB).  A-fragment and B-fragment
+//     of a tile are the same register.
+//   * Two accumulator sets: the segment's (flushed per segment through a 2 KB shared scratch: W by coalesced plain
+//     stores -- the warp owns the segment -- V/g_m by FP64 reductions) and the camera's (U_c, g_c, r.r; flushed when
+//     the camera changes).
+//   * k_normal_epilogue applies the SO(3) left Jacobians once per block (tangent -> rvec parametrisation).
 //   HBM traffic per observation: (u,v) 16 B + camera, pose, key 12 B = 28 B read; outputs are O(segments).
 #include <algorithm>
 #include <cstdlib>
@@ -30,7 +35,8 @@ namespace pcs {
 
 constexpr int NE_WARPS = 4;                  // warps per CTA
 constexpr int NE_TILE_DOUBLES = 64 * 8;      // one 8-column tile of the 64 staged rows
-constexpr int NE_WARP_DOUBLES = 3 * NE_TILE_DOUBLES;
+constexpr int NE_SCRATCH_DOUBLES = 16 * 16 + 36 + 36;   // G_s | T | E T
+constexpr int NE_WARP_DOUBLES = 2 * NE_TILE_DOUBLES + NE_SCRATCH_DOUBLES;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
 {
@@ -49,73 +55,132 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 __device__ __forceinline__ int stage_row(int o, int r) { return (2 * o + (r ^ ((o >> 1) & 1))) * 8; }
 __device__ __forceinline__ int stage_rot(int o) { return 4 * (o & 1) + 2 * ((o >> 2) & 1); }
 
-__device__ __forceinline__ void stage_store_row(double* __restrict__ row, int rot, const double t0[8], const double t1[8],
-                                                const double t2[8])
+__device__ __forceinline__ void stage_store_row(double* __restrict__ row, int rot, const double t0[8], const double t1[8])
 {
 #pragma unroll
     for (int c = 0; c < 8; c += 2) {
         const int pos = c ^ rot;
         *reinterpret_cast<double2*>(row + pos) = make_double2(t0[c], t0[c + 1]);
         *reinterpret_cast<double2*>(row + NE_TILE_DOUBLES + pos) = make_double2(t1[c], t1[c + 1]);
-        *reinterpret_cast<double2*>(row + 2 * NE_TILE_DOUBLES + pos) = make_double2(t2[c], t2[c + 1]);
     }
 }
 
+// Fragment (m8n8 accumulator) layout: lane holds rows lane >> 2, columns 2 (lane & 3) + {0, 1} of an 8 x 8 tile.
+// Column order of the 16 accumulated columns: 0..14 = camera (9 intrinsic, 3 rotation (tangent), 3 translation), 15 = r.
 struct NeAcc {
-    double a00[2], a01[2], a02[2];  // per-segment tiles (row 6 = g_c / cost keeps accumulating)
-    double a11[2], a12[2], a22[2];  // per-camera tiles
+    double aa[2], ab[2], bb[2];
 };
 
-// V_m, g_m (reductions), W_{c,m} (plain stores: this warp owns the whole segment); resets what it flushed.
-__device__ __forceinline__ void flush_segment(NeAcc& A, int lane, int64_t seg, int m, double* __restrict__ V,
-                                              double* __restrict__ gp, double* __restrict__ W)
-{
-    const int row = lane >> 2, cp = 2 * (lane & 3);
-    if (row < 6) {
-        double* Vm = V + (int64_t)m * 36 + row * 6;
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (cp + i < 6) atomicAdd(Vm + cp + i, A.a00[i]);
-        double* Ws = W + seg * 90 + row;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            Ws[(cp + i) * 6] = A.a01[i];
-            if (8 + cp + i < 15) Ws[(8 + cp + i) * 6] = A.a02[i];
-        }
-        A.a00[0] = A.a00[1] = A.a01[0] = A.a01[1] = A.a02[0] = A.a02[1] = 0.0;
-    } else if (row == 6) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (cp + i < 6) {
-                atomicAdd(gp + (int64_t)m * 6 + cp + i, A.a00[i]);
-                A.a00[i] = 0.0;
-            }
-    } else {
-        A.a00[0] = A.a00[1] = A.a01[0] = A.a01[1] = A.a02[0] = A.a02[1] = 0.0;
-    }
-}
+__device__ __forceinline__ void acc_zero(NeAcc& A) { A.aa[0] = A.aa[1] = A.ab[0] = A.ab[1] = A.bb[0] = A.bb[1] = 0.0; }
 
-// U_c (both triangles) and g_c
-__device__ __forceinline__ void flush_camera(NeAcc& A, int lane, int c, double* __restrict__ U, double* __restrict__ gc)
+// Segment flush.  S = this segment's camera Gram matrix (fragments), C = the running camera sums.
+// scratch: G[16][16] | T[6][6] | ET[6][6].
+__device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int64_t seg, int c, int m,
+                                              const double* __restrict__ camtab, const double* __restrict__ posetab,
+                                              double* __restrict__ scratch, double* __restrict__ V, double* __restrict__ gp,
+                                              double* __restrict__ W)
 {
+    double* const G = scratch;
+    double* const T = scratch + 256;
+    double* const ET = scratch + 292;
     const int row = lane >> 2, cp = 2 * (lane & 3);
-    double* Uc = U + (int64_t)c * 225;
+    // (1) the segment's full symmetric 16 x 16 matrix; fold the segment into the camera sums
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int col = cp + i;
-        atomicAdd(Uc + row * 15 + col, A.a11[i]);
-        if (8 + col < 15) {
-            atomicAdd(Uc + row * 15 + 8 + col, A.a12[i]);
-            atomicAdd(Uc + (8 + col) * 15 + row, A.a12[i]);
-            if (row < 7) atomicAdd(Uc + (8 + row) * 15 + 8 + col, A.a22[i]);
-        }
-        if (row == 6) {
-            atomicAdd(gc + (int64_t)c * 15 + col, A.a01[i]);
-            if (8 + col < 15) atomicAdd(gc + (int64_t)c * 15 + 8 + col, A.a02[i]);
-            A.a01[i] = A.a02[i] = 0.0;
-        }
-        A.a11[i] = A.a12[i] = A.a22[i] = 0.0;
+        G[row * 16 + col] = S.aa[i];
+        G[row * 16 + 8 + col] = S.ab[i];
+        G[(8 + col) * 16 + row] = S.ab[i];
+        G[(8 + row) * 16 + 8 + col] = S.bb[i];
+        C.aa[i] += S.aa[i]; C.ab[i] += S.ab[i]; C.bb[i] += S.bb[i];
     }
+    acc_zero(S);
+    // (2) adjoint T = [[R_c, 0], [[s]x R_c, R_c]], s = R_c t_m
+    if (lane < 9) {
+        const double* Rc = camtab + (int64_t)c * CAM_STRIDE + CAM_R;
+        const double* tm = posetab + (int64_t)m * POSE_STRIDE + POSE_T;
+        const int i = lane / 3, j = lane - 3 * i;
+        const double t0 = tm[0], t1 = tm[1], t2 = tm[2];
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        // ([s]x R_c)[i][j] = s_{i+1} R[i+2][j] - s_{i+2} R[i+1][j]  with cyclic indices
+        const double s1 = Rc[3 * i1] * t0 + Rc[3 * i1 + 1] * t1 + Rc[3 * i1 + 2] * t2;
+        const double s2 = Rc[3 * i2] * t0 + Rc[3 * i2 + 1] * t1 + Rc[3 * i2 + 2] * t2;
+        const double r = Rc[3 * i + j];
+        T[i * 6 + j] = r;
+        T[i * 6 + 3 + j] = 0.0;
+        T[(3 + i) * 6 + j] = s1 * Rc[3 * i2 + j] - s2 * Rc[3 * i1 + j];
+        T[(3 + i) * 6 + 3 + j] = r;
+    }
+    __syncwarp();
+    // (3) W_s = G[0:15, 9:15] T  (90 entries, stored with consecutive addresses);  ET = G[9:15, 9:15] T
+    double* Ws = W + seg * 90;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 90) {
+            const int a = idx / 6, j = idx - 6 * a;
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v = fma(G[a * 16 + 9 + k], T[k * 6 + j], v);
+            Ws[idx] = v;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 36) {
+            const int i = idx / 6, j = idx - 6 * i;
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v = fma(G[(9 + i) * 16 + 9 + k], T[k * 6 + j], v);
+            ET[idx] = v;
+        }
+    }
+    __syncwarp();
+    // (4) V_m += T^T ET,  g_m += T^T G[9:15, 15]
+    double* Vm = V + (int64_t)m * 36;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int idx = lane + 32 * t;
+        if (idx < 36) {
+            const int i = idx / 6, j = idx - 6 * i;
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v = fma(T[k * 6 + i], ET[k * 6 + j], v);
+            atomicAdd(Vm + idx, v);
+        } else if (idx < 42) {
+            const int j = idx - 36;
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v = fma(T[k * 6 + j], G[(9 + k) * 16 + 15], v);
+            atomicAdd(gp + (int64_t)m * 6 + j, v);
+        }
+    }
+    __syncwarp();  // scratch is reused by the next flush
+}
+
+// Camera flush: U_c (both triangles), g_c and r.r from the running camera sums
+__device__ __forceinline__ void flush_camera(NeAcc& C, int lane, int c, double* __restrict__ U, double* __restrict__ gc,
+                                             double* __restrict__ cost)
+{
+    const int row = lane >> 2, cp = 2 * (lane & 3);
+    double* Uc = U + (int64_t)c * 225;
+    double* gcc = gc + (int64_t)c * 15;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int col = cp + i;
+        atomicAdd(Uc + row * 15 + col, C.aa[i]);
+        if (col < 7) {
+            atomicAdd(Uc + row * 15 + 8 + col, C.ab[i]);
+            atomicAdd(Uc + (8 + col) * 15 + row, C.ab[i]);
+            if (row < 7) atomicAdd(Uc + (8 + row) * 15 + 8 + col, C.bb[i]);
+        } else {
+            atomicAdd(gcc + row, C.ab[i]);
+            if (row < 7) atomicAdd(gcc + 8 + row, C.bb[i]);
+            else atomicAdd(cost, C.bb[i]);
+        }
+    }
+    acc_zero(C);
 }
 
 template <int CTAS_PER_SM>
@@ -137,9 +202,10 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     if (sb >= se) return;
     const int64_t begin = seg_start[sb], end = seg_start[se];
 
-    NeAcc A;
-    A.a00[0] = A.a00[1] = A.a01[0] = A.a01[1] = A.a02[0] = A.a02[1] = 0.0;
-    A.a11[0] = A.a11[1] = A.a12[0] = A.a12[1] = A.a22[0] = A.a22[1] = 0.0;
+    NeAcc S, C;   // segment / camera accumulators
+    acc_zero(S);
+    acc_zero(C);
+    double* const scratch = ws + 2 * NE_TILE_DOUBLES;
     int64_t cur_seg = sb - 1;   // segments are visited in order: a piece head advances this counter
     int cur_c = -1, cur_m = -1;
     int last_c = -1, last_m = -1;  // (camera, pose) of the last observation of the previous batch
@@ -172,19 +238,17 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
             const double* ct = camtab + (int64_t)c * CAM_STRIDE;
             const double* ptab = posetab + (int64_t)m * POSE_STRIDE;
             double res[2];
-            ObsJac J;
-            eval_obs(ct, ptab, Xt, o.x, o.y, res, J);
+            ObsJacCam J;
+            eval_obs_cam(ct, ptab, Xt, o.x, o.y, res, J);
             {
-                const double t0[8] = {J.Wm[0], J.Wm[1], J.Wm[2], J.N[0], J.N[1], J.N[2], res[0], 0.0};
-                const double t1[8] = {J.xD, 1.0, 0.0, 0.0, J.Au[0], J.Au[1], J.Au[2], J.Au[3]};
-                const double t2[8] = {J.Au[4], J.Wc[0], J.Wc[1], J.Wc[2], J.Pm[0], J.Pm[1], J.Pm[2], 0.0};
-                stage_store_row(st_u, st_rot, t0, t1, t2);
+                const double t0[8] = {J.xD, 1.0, 0.0, 0.0, J.Au[0], J.Au[1], J.Au[2], J.Au[3]};
+                const double t1[8] = {J.Au[4], J.Wc[0], J.Wc[1], J.Wc[2], J.Pm[0], J.Pm[1], J.Pm[2], res[0]};
+                stage_store_row(st_u, st_rot, t0, t1);
             }
             {
-                const double t0[8] = {J.Wm[3], J.Wm[4], J.Wm[5], J.N[3], J.N[4], J.N[5], res[1], 0.0};
-                const double t1[8] = {0.0, 0.0, J.yD, 1.0, J.Av[0], J.Av[1], J.Av[2], J.Av[3]};
-                const double t2[8] = {J.Av[4], J.Wc[3], J.Wc[4], J.Wc[5], J.Pm[3], J.Pm[4], J.Pm[5], 0.0};
-                stage_store_row(st_v, st_rot, t0, t1, t2);
+                const double t0[8] = {0.0, 0.0, J.yD, 1.0, J.Av[0], J.Av[1], J.Av[2], J.Av[3]};
+                const double t1[8] = {J.Av[4], J.Wc[3], J.Wc[4], J.Wc[5], J.Pm[3], J.Pm[4], J.Pm[5], res[1]};
+                stage_store_row(st_v, st_rot, t0, t1);
             }
         }
         // piece heads: lanes whose (camera, pose) differs from the previous observation's
@@ -200,34 +264,30 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
             pieces &= pieces - 1;
             const int b = pieces ? __ffs(pieces) - 1 : cnt;
             if ((heads >> a) & 1u) {
-                if (cur_c >= 0) flush_segment(A, lane, cur_seg, cur_m, V, gp, W);
+                if (cur_c >= 0) flush_segment(S, C, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, V, gp, W);
                 const int nc = __shfl_sync(0xffffffffu, c, a);
-                if (nc != cur_c && cur_c >= 0) flush_camera(A, lane, cur_c, U, gc);
+                if (nc != cur_c && cur_c >= 0) flush_camera(C, lane, cur_c, U, gc, cost);
                 ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
             }
             const int k0 = a >> 1, k1 = (b - 1) >> 1;
             for (int ks = k0; ks <= k1; ++ks) {
                 const double* f = ws + 32 * ks + (ld_L ^ (((ks & 1) << 3) | (ks & 2)));
-                double v0 = f[0], v1 = f[NE_TILE_DOUBLES], v2 = f[2 * NE_TILE_DOUBLES];
+                double v0 = f[0], v1 = f[NE_TILE_DOUBLES];
                 if (ks == k0 || ks == k1) {  // boundary k-steps may hold rows of a neighbouring segment (or stale rows)
                     const int ob = 2 * ks + jb;
                     const bool ok = ob >= a && ob < b;
-                    v0 = ok ? v0 : 0.0; v1 = ok ? v1 : 0.0; v2 = ok ? v2 : 0.0;
+                    v0 = ok ? v0 : 0.0; v1 = ok ? v1 : 0.0;
                 }
-                dmma884(A.a00[0], A.a00[1], v0, v0);
-                dmma884(A.a01[0], A.a01[1], v0, v1);
-                dmma884(A.a02[0], A.a02[1], v0, v2);
-                dmma884(A.a11[0], A.a11[1], v1, v1);
-                dmma884(A.a12[0], A.a12[1], v1, v2);
-                dmma884(A.a22[0], A.a22[1], v2, v2);
+                dmma884(S.aa[0], S.aa[1], v0, v0);
+                dmma884(S.ab[0], S.ab[1], v0, v1);
+                dmma884(S.bb[0], S.bb[1], v1, v1);
             }
         }
         __syncwarp();
     }
     if (cur_c >= 0) {
-        flush_segment(A, lane, cur_seg, cur_m, V, gp, W);
-        flush_camera(A, lane, cur_c, U, gc);
-        if (lane == 27) atomicAdd(cost, A.a00[0]);  // row 6, column 6 of tile (0,0) = r . r
+        flush_segment(S, C, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, V, gp, W);
+        flush_camera(C, lane, cur_c, U, gc, cost);
     }
 }
 
