@@ -35,7 +35,7 @@ namespace pcs {
 
 constexpr int NE_WARPS = 4;                  // warps per CTA
 constexpr int NE_TILE_DOUBLES = 64 * 8;      // one 8-column tile of the 64 staged rows
-constexpr int NE_SCRATCH_DOUBLES = 16 * 16 + 36 + 36;   // G_s | T | E T
+constexpr int NE_SCRATCH_DOUBLES = 64;                 // Tbar (8 x 8), see flush_segment
 constexpr int NE_WARP_DOUBLES = 2 * NE_TILE_DOUBLES + NE_SCRATCH_DOUBLES;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
@@ -73,90 +73,88 @@ struct NeAcc {
 
 __device__ __forceinline__ void acc_zero(NeAcc& A) { A.aa[0] = A.aa[1] = A.ab[0] = A.ab[1] = A.bb[0] = A.bb[1] = 0.0; }
 
-// Segment flush.  S = this segment's camera Gram matrix (fragments), C = the running camera sums.
-// scratch: G[16][16] | T[6][6] | ET[6][6].
+// double-precision shuffle of one of two registers: returns (sel ? x1 : x0) of lane `src`
+__device__ __forceinline__ double shfl_pick(double x0, double x1, int src, bool sel)
+{
+    const double y0 = __shfl_sync(0xffffffffu, x0, src), y1 = __shfl_sync(0xffffffffu, x1, src);
+    return sel ? y1 : y0;
+}
+
+// D (8 x 8, accumulator layout) = X (8 x 8, accumulator layout) * Tbar (8 x 8), as two DMMA k-steps; tb0 / tb1 are
+// the lane's Tbar fragments for k = 0..3 / 4..7 (Tbar[4h + (lane & 3)][lane >> 2]).
+__device__ __forceinline__ void tile_times_tbar(const double x[2], double tb0, double tb1, int lane, double d[2])
+{
+    d[0] = d[1] = 0.0;
+    // A fragment element (row = lane >> 2, k = 4h + (lane & 3)) sits in lane (row * 4 + k / 2), register k & 1
+    const int quad = lane & ~3, half = (lane & 3) >> 1;
+    const bool odd = lane & 1;
+    const double a0 = shfl_pick(x[0], x[1], quad + half, odd);
+    const double a1 = shfl_pick(x[0], x[1], quad + 2 + half, odd);
+    dmma884(d[0], d[1], a0, tb0);
+    dmma884(d[0], d[1], a1, tb1);
+}
+
+// Segment flush.  S = this segment's camera Gram matrix G_s (fragments: aa = G[0:8,0:8], ab = G[0:8,8:16],
+// bb = G[8:16,8:16]; column 8 + kk with kk = 0: k3, 1..3: camera rotation (tangent), 4..6: camera translation, 7: r).
+// C = the running camera sums.  With the adjoint folded with the pose's left Jacobian,
+//     T' = [[R_c Jl_m, 0], [[s]x R_c Jl_m, R_c]],  s = R_c t_m,
+// embedded as Tbar[1..6][0..5] = T', Tbar[7][6] = 1 (zero elsewhere), the pose blocks are three small products
+// on the FP64 tensor path:
+//     Wbar_A = ab Tbar, Wbar_B = bb Tbar   -> W_s[a][j] (a < 15, j < 6), final in the pose columns
+//     Vbar   = Tbar^T Wbar_B               -> V_m += Vbar[0:6,0:6], g_m += Vbar[0:6,6]
+// (rows 9..11 of W_s still need the camera's left Jacobian: k_normal_epilogue).
 __device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int64_t seg, int c, int m,
                                               const double* __restrict__ camtab, const double* __restrict__ posetab,
-                                              double* __restrict__ scratch, double* __restrict__ V, double* __restrict__ gp,
+                                              double* __restrict__ tbar, double* __restrict__ V, double* __restrict__ gp,
                                               double* __restrict__ W)
 {
-    double* const G = scratch;
-    double* const T = scratch + 256;
-    double* const ET = scratch + 292;
-    const int row = lane >> 2, cp = 2 * (lane & 3);
-    // (1) the segment's full symmetric 16 x 16 matrix; fold the segment into the camera sums
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int col = cp + i;
-        G[row * 16 + col] = S.aa[i];
-        G[row * 16 + 8 + col] = S.ab[i];
-        G[(8 + col) * 16 + row] = S.ab[i];
-        G[(8 + row) * 16 + 8 + col] = S.bb[i];
-        C.aa[i] += S.aa[i]; C.ab[i] += S.ab[i]; C.bb[i] += S.bb[i];
-    }
-    acc_zero(S);
-    // (2) adjoint T = [[R_c, 0], [[s]x R_c, R_c]], s = R_c t_m
     if (lane < 9) {
         const double* Rc = camtab + (int64_t)c * CAM_STRIDE + CAM_R;
-        const double* tm = posetab + (int64_t)m * POSE_STRIDE + POSE_T;
+        const double* pm = posetab + (int64_t)m * POSE_STRIDE;
         const int i = lane / 3, j = lane - 3 * i;
-        const double t0 = tm[0], t1 = tm[1], t2 = tm[2];
         const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-        // ([s]x R_c)[i][j] = s_{i+1} R[i+2][j] - s_{i+2} R[i+1][j]  with cyclic indices
+        const double t0 = pm[POSE_T], t1 = pm[POSE_T + 1], t2 = pm[POSE_T + 2];
+        const double j0 = pm[POSE_JL + j], j1 = pm[POSE_JL + 3 + j], j2 = pm[POSE_JL + 6 + j];
         const double s1 = Rc[3 * i1] * t0 + Rc[3 * i1 + 1] * t1 + Rc[3 * i1 + 2] * t2;
         const double s2 = Rc[3 * i2] * t0 + Rc[3 * i2 + 1] * t1 + Rc[3 * i2 + 2] * t2;
-        const double r = Rc[3 * i + j];
-        T[i * 6 + j] = r;
-        T[i * 6 + 3 + j] = 0.0;
-        T[(3 + i) * 6 + j] = s1 * Rc[3 * i2 + j] - s2 * Rc[3 * i1 + j];
-        T[(3 + i) * 6 + 3 + j] = r;
+        const double q = Rc[3 * i] * j0 + Rc[3 * i + 1] * j1 + Rc[3 * i + 2] * j2;        // (R_c Jl_m)[i][j]
+        const double q1 = Rc[3 * i1] * j0 + Rc[3 * i1 + 1] * j1 + Rc[3 * i1 + 2] * j2;
+        const double q2 = Rc[3 * i2] * j0 + Rc[3 * i2 + 1] * j1 + Rc[3 * i2 + 2] * j2;
+        tbar[(1 + i) * 8 + j] = q;
+        tbar[(4 + i) * 8 + j] = s1 * q2 - s2 * q1;                                          // ([s]x R_c Jl_m)[i][j]
+        tbar[(4 + i) * 8 + 3 + j] = Rc[3 * i + j];
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { C.aa[i] += S.aa[i]; C.ab[i] += S.ab[i]; C.bb[i] += S.bb[i]; }
     __syncwarp();
-    // (3) W_s = G[0:15, 9:15] T  (90 entries, stored with consecutive addresses);  ET = G[9:15, 9:15] T
-    double* Ws = W + seg * 90;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        const int idx = lane + 32 * t;
-        if (idx < 90) {
-            const int a = idx / 6, j = idx - 6 * a;
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) v = fma(G[a * 16 + 9 + k], T[k * 6 + j], v);
-            Ws[idx] = v;
-        }
+    const double tb0 = tbar[(lane & 3) * 8 + (lane >> 2)], tb1 = tbar[(4 + (lane & 3)) * 8 + (lane >> 2)];
+    double wa[2], wb[2];
+    tile_times_tbar(S.ab, tb0, tb1, lane, wa);
+    tile_times_tbar(S.bb, tb0, tb1, lane, wb);
+    // Vbar = Tbar^T Wbar_B: the A fragment of Tbar^T is the same register as the B fragment of Tbar;
+    // B fragment element (k = 4h + (lane & 3), n = lane >> 2) of Wbar_B sits in lane (k * 4 + n / 2), register n & 1
+    double vb[2] = {0.0, 0.0};
+    {
+        const int n = lane >> 2;
+        const bool odd = n & 1;
+        const double b0 = shfl_pick(wb[0], wb[1], (lane & 3) * 4 + (n >> 1), odd);
+        const double b1 = shfl_pick(wb[0], wb[1], (4 + (lane & 3)) * 4 + (n >> 1), odd);
+        dmma884(vb[0], vb[1], tb0, b0);
+        dmma884(vb[0], vb[1], tb1, b1);
     }
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const int idx = lane + 32 * t;
-        if (idx < 36) {
-            const int i = idx / 6, j = idx - 6 * i;
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) v = fma(G[(9 + i) * 16 + 9 + k], T[k * 6 + j], v);
-            ET[idx] = v;
+    const int row = lane >> 2, cp = 2 * (lane & 3);
+    if (cp < 6) {   // W_s[a][cp], W_s[a][cp + 1]: 16-byte stores
+        double* Ws = W + seg * 90 + cp;
+        *reinterpret_cast<double2*>(Ws + row * 6) = make_double2(wa[0], wa[1]);
+        if (row < 7) *reinterpret_cast<double2*>(Ws + (8 + row) * 6) = make_double2(wb[0], wb[1]);
+        if (row < 6) {
+            atomicAdd(V + (int64_t)m * 36 + row * 6 + cp, vb[0]);
+            atomicAdd(V + (int64_t)m * 36 + row * 6 + cp + 1, vb[1]);
         }
+    } else if (row < 6) {
+        atomicAdd(gp + (int64_t)m * 6 + row, vb[0]);   // column 6 of Vbar
     }
-    __syncwarp();
-    // (4) V_m += T^T ET,  g_m += T^T G[9:15, 15]
-    double* Vm = V + (int64_t)m * 36;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const int idx = lane + 32 * t;
-        if (idx < 36) {
-            const int i = idx / 6, j = idx - 6 * i;
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) v = fma(T[k * 6 + i], ET[k * 6 + j], v);
-            atomicAdd(Vm + idx, v);
-        } else if (idx < 42) {
-            const int j = idx - 36;
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) v = fma(T[k * 6 + j], G[(9 + k) * 16 + 15], v);
-            atomicAdd(gp + (int64_t)m * 6 + j, v);
-        }
-    }
-    __syncwarp();  // scratch is reused by the next flush
+    acc_zero(S);
 }
 
 // Camera flush: U_c (both triangles), g_c and r.r from the running camera sums
@@ -205,7 +203,10 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     NeAcc S, C;   // segment / camera accumulators
     acc_zero(S);
     acc_zero(C);
-    double* const scratch = ws + 2 * NE_TILE_DOUBLES;
+    double* const scratch = ws + 2 * NE_TILE_DOUBLES;   // Tbar: constant entries are written once
+    scratch[lane] = 0.0;
+    scratch[32 + lane] = lane == 30 ? 1.0 : 0.0;       // Tbar[7][6] = 1
+    __syncwarp();
     int64_t cur_seg = sb - 1;   // segments are visited in order: a piece head advances this counter
     int cur_c = -1, cur_m = -1;
     int last_c = -1, last_m = -1;  // (camera, pose) of the last observation of the previous batch
@@ -304,16 +305,14 @@ __global__ void k_warp_ranges(int64_t N, int64_t n_seg, int n_warps, const int64
     warp_seg[w] = w == n_warps ? n_seg : lo;
 }
 
-// Epilogue: the kernel above accumulates the rotation rows / columns in the tangent parametrisation; this maps the
-// blocks to the reference's rvec parametrisation, B = T^T B' T with T_c = diag(I9, Jl_c, I3), T_m = diag(Jl_m, I3).
-//   blocks [0, C)            : U_c, g_c   (one block of 64 threads per camera)
-//   blocks [C, C + Pb)       : V_m, g_m   (one thread per pose)
-//   blocks [C + Pb, ...)     : W_s        (15 lanes per segment, 2 segments per warp)
+// Epilogue: the camera-rotation rows / columns are accumulated in the tangent parametrisation; this maps them to the
+// reference's rvec parametrisation with the camera's left Jacobian, B = T^T B' T, T_c = diag(I9, Jl_c, I3).
+// (The pose side is final already: flush_segment folds Jl_m into the adjoint.)
+//   blocks [0, C)   : U_c, g_c            (one block of 64 threads per camera)
+//   blocks [C, ...) : rows 9..11 of W_s   (6 threads per segment: one per pose column; 144 contiguous bytes)
 __global__ void __launch_bounds__(64)
-k_normal_epilogue(int C, int M, int64_t n_seg, int pose_blocks, const int32_t* __restrict__ seg_cam,
-                  const int32_t* __restrict__ seg_pose, const double* __restrict__ camtab, const double* __restrict__ posetab,
-                  double* __restrict__ U, double* __restrict__ gc, double* __restrict__ V, double* __restrict__ gp,
-                  double* __restrict__ W)
+k_normal_epilogue(int C, int64_t n_seg, const int32_t* __restrict__ seg_cam, const double* __restrict__ camtab,
+                  double* __restrict__ U, double* __restrict__ gc, double* __restrict__ W)
 {
     const int t = threadIdx.x;
     if ((int)blockIdx.x < C) {
@@ -344,70 +343,15 @@ k_normal_epilogue(int C, int M, int64_t n_seg, int pose_blocks, const int32_t* _
         for (int e = t; e < 225; e += 64) Uc[e] = u[e];
         return;
     }
-    if ((int)blockIdx.x < C + pose_blocks) {
-        const int m = ((int)blockIdx.x - C) * 64 + t;
-        if (m >= M) return;
-        const double* jl = posetab + (int64_t)m * POSE_STRIDE + POSE_JL;
-        const double j[9] = {jl[0], jl[1], jl[2], jl[3], jl[4], jl[5], jl[6], jl[7], jl[8]};
-        double* Vm = V + (int64_t)m * 36;
-        double v[36];
+    const int64_t idx = ((int64_t)blockIdx.x - C) * 64 + t;
+    const int64_t s = idx / 6;
+    if (s >= n_seg) return;
+    const int j = (int)(idx - 6 * s);
+    const double* jl = camtab + (int64_t)seg_cam[s] * CAM_STRIDE + CAM_JL;
+    double* w = W + s * 90 + 54 + j;   // rows 9, 10, 11 of column j
+    const double a0 = w[0], a1 = w[6], a2 = w[12];
 #pragma unroll
-        for (int e = 0; e < 36; ++e) v[e] = Vm[e];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const double a0 = v[r * 6], a1 = v[r * 6 + 1], a2 = v[r * 6 + 2];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) v[r * 6 + i] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
-        }
-#pragma unroll
-        for (int cidx = 0; cidx < 6; ++cidx) {
-            const double a0 = v[cidx], a1 = v[6 + cidx], a2 = v[12 + cidx];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) v[i * 6 + cidx] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
-        }
-#pragma unroll
-        for (int e = 0; e < 36; ++e) Vm[e] = v[e];
-        double* g = gp + (int64_t)m * 6;
-        const double a0 = g[0], a1 = g[1], a2 = g[2];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) g[i] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
-        return;
-    }
-    // W_s (15 x 6): lane a of a 15-lane group owns row a
-    const int64_t wblock = (int64_t)blockIdx.x - C - pose_blocks;
-    const int lane = t & 31, grp = lane / 15, a = lane % 15;
-    const int64_t s = (wblock * 2 + (t >> 5)) * 2 + grp;
-    const bool active = grp < 2 && s < n_seg;
-    double r[6] = {0, 0, 0, 0, 0, 0};
-    const int k = a - 9;  // 0..2 for the camera-rotation rows
-    double jk0 = 0.0, jk1 = 0.0, jk2 = 0.0;  // column k of Jl_c
-    if (active) {
-        const double* jm = posetab + (int64_t)seg_pose[s] * POSE_STRIDE + POSE_JL;
-        const double* Ws = W + s * 90 + a * 6;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) r[i] = Ws[i];
-        const double a0 = r[0], a1 = r[1], a2 = r[2];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] = a0 * jm[i] + a1 * jm[3 + i] + a2 * jm[6 + i];
-        if (k >= 0 && k < 3) {
-            const double* jcp = camtab + (int64_t)seg_cam[s] * CAM_STRIDE + CAM_JL;
-            jk0 = jcp[k]; jk1 = jcp[3 + k]; jk2 = jcp[6 + k];
-        }
-    }
-    // rows 9..11 mix: new row (9 + i) = sum_i' Jl_c[i'][i] row (9 + i')
-    const int src0 = grp * 15 + 9;
-    double out[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const double x0 = __shfl_sync(0xffffffffu, r[i], src0 & 31), x1 = __shfl_sync(0xffffffffu, r[i], (src0 + 1) & 31),
-                     x2 = __shfl_sync(0xffffffffu, r[i], (src0 + 2) & 31);
-        out[i] = (k >= 0 && k < 3) ? x0 * jk0 + x1 * jk1 + x2 * jk2 : r[i];
-    }
-    if (active) {
-        double* Ws = W + s * 90 + a * 6;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Ws[i] = out[i];
-    }
+    for (int i = 0; i < 3; ++i) w[6 * i] = a0 * jl[i] + a1 * jl[3 + i] + a2 * jl[6 + i];
 }
 
 static int ensure_ranges(pcs_problem* p, int64_t n_ranges)
@@ -430,8 +374,8 @@ int launch_normal_blocks(pcs_problem* p)
     PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
     if (p->N == 0) return PCS_OK;
     // resident CTAs per SM: 4 x 128 registers (default) or 3 x 154; PCS_NE_CTAS=3 selects the latter for A/B runs
-    static const int ctas = [] { const char* e = std::getenv("PCS_NE_CTAS"); return e && e[0] == '3' ? 3 : 4; }();
-    auto kern = ctas == 3 ? k_normal<3> : k_normal<4>;
+    static const int ctas = [] { const char* e = std::getenv("PCS_NE_CTAS"); return e && e[0] >= '3' && e[0] <= '5' ? e[0] - '0' : 4; }();
+    auto kern = ctas == 3 ? k_normal<3> : ctas == 5 ? k_normal<5> : k_normal<4>;
     static bool attr_set = false;
     const size_t smem = (size_t)NE_WARPS * NE_WARP_DOUBLES * sizeof(double);
     if (!attr_set) {
@@ -448,10 +392,9 @@ int launch_normal_blocks(pcs_problem* p)
                                                   (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab, p->tmpl,
                                                   p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
-    const int pose_blocks = (p->M + 63) / 64;
-    const int64_t w_blocks = (p->n_seg + 3) / 4;
-    k_normal_epilogue<<<(unsigned)(p->C + pose_blocks + w_blocks), 64, 0, p->stream>>>(
-        p->C, p->M, p->n_seg, pose_blocks, p->seg_cam, p->seg_pose, p->camtab, p->posetab, p->U, p->gc, p->V, p->gp, p->W);
+    const int64_t w_blocks = (p->n_seg * 6 + 63) / 64;
+    k_normal_epilogue<<<(unsigned)(p->C + w_blocks), 64, 0, p->stream>>>(p->C, p->n_seg, p->seg_cam, p->camtab, p->U, p->gc,
+                                                                        p->W);
     PCS_CUDA(cudaGetLastError());
     p->n_launches += 2;
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_b, p->stream));
