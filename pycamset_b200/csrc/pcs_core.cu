@@ -60,15 +60,37 @@ __global__ void k_scatter_x(int64_t n_free, const int32_t* __restrict__ free_idx
 // Per-camera / per-pose tables: rotation matrices and their derivatives are computed ONCE per parameter
 // update instead of once per observation (the reference calls Rodrigues inside the per-observation loop,
 // function_block_implementations.py:150-182).
-__global__ void k_prepare_tables(int C, int M, const double* __restrict__ params, double* __restrict__ camtab,
-                                 double* __restrict__ posetab, double* __restrict__ dRtab)
+// Optionally fused into the same launch (the normal-equation evaluation runs it every step):
+//   x != nullptr   : scatter the free vector into the parameter string first (fill_flat, compiled_helpers.py:155-177);
+//                    threads [C + M, C + M + n_tail) handle the entries after the pose block (free points, chain 1)
+//   zero != nullptr: clear `n_zero` doubles (the reduction targets of the normal-equation kernel)
+__device__ __forceinline__ double param_value(double* __restrict__ params, const double* __restrict__ x,
+                                              const int32_t* __restrict__ free_map, int64_t i)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x) {
+        const int32_t f = free_map[i];
+        if (f >= 0) {
+            const double v = x[f];
+            params[i] = v;
+            return v;
+        }
+    }
+    return params[i];
+}
+
+__global__ void k_prepare_tables(int C, int M, int64_t n_tail, double* __restrict__ params, const double* __restrict__ x,
+                                 const int32_t* __restrict__ free_map, double* __restrict__ camtab,
+                                 double* __restrict__ posetab, double* __restrict__ dRtab, double* __restrict__ zero,
+                                 int64_t n_zero)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t i = t; i < n_zero; i += (int64_t)gridDim.x * blockDim.x) zero[i] = 0.0;
     if (t < C) {
-        const double* q = params + 9 * (int64_t)t;
-        const double* e = params + 9 * (int64_t)C + 6 * (int64_t)t;
-        double* o = camtab + (int64_t)t * CAM_STRIDE;
-        for (int k = 0; k < 9; ++k) o[CAM_Q + k] = q[k];
+        const int64_t qi = 9 * t, ei = 9 * (int64_t)C + 6 * t;
+        double* o = camtab + t * CAM_STRIDE;
+        for (int k = 0; k < 9; ++k) o[CAM_Q + k] = param_value(params, x, free_map, qi + k);
+        double e[6];
+        for (int k = 0; k < 6; ++k) e[k] = param_value(params, x, free_map, ei + k);
         double r[3] = {e[0], e[1], e[2]}, R[9], Jl[9];
         rodrigues(r, R);
         rodrigues_left_jacobian(r, Jl);
@@ -76,11 +98,13 @@ __global__ void k_prepare_tables(int C, int M, const double* __restrict__ params
         for (int k = 0; k < 3; ++k) o[CAM_T + k] = e[3 + k];
         for (int k = 0; k < 9; ++k) o[CAM_JL + k] = Jl[k];
         o[30] = o[31] = 0.0;
-        if (dRtab) rodrigues_jac(r, dRtab + 27 * (int64_t)t);
+        if (dRtab) rodrigues_jac(r, dRtab + 27 * t);
     } else if (t < C + M) {
-        int m = t - C;
-        const double* e = params + 15 * (int64_t)C + 6 * (int64_t)m;
-        double* o = posetab + (int64_t)m * POSE_STRIDE;
+        const int64_t m = t - C;
+        const int64_t ei = 15 * (int64_t)C + 6 * m;
+        double* o = posetab + m * POSE_STRIDE;
+        double e[6];
+        for (int k = 0; k < 6; ++k) e[k] = param_value(params, x, free_map, ei + k);
         double r[3] = {e[0], e[1], e[2]}, R[9], Jl[9];
         rodrigues(r, R);
         rodrigues_left_jacobian(r, Jl);
@@ -88,7 +112,9 @@ __global__ void k_prepare_tables(int C, int M, const double* __restrict__ params
         for (int k = 0; k < 3; ++k) o[POSE_T + k] = e[3 + k];
         for (int k = 0; k < 9; ++k) o[POSE_JL + k] = Jl[k];
         o[21] = o[22] = o[23] = 0.0;
-        if (dRtab) rodrigues_jac(r, dRtab + 27 * (int64_t)t);
+        if (dRtab) rodrigues_jac(r, dRtab + 27 * t);
+    } else if (x && t < (int64_t)C + M + n_tail) {
+        param_value(params, x, free_map, 15 * (int64_t)C + 6 * (int64_t)M + (t - C - M));
     }
 }
 
@@ -102,12 +128,16 @@ int launch_scatter_x(pcs_problem* p, const double* x_dev)
     return PCS_OK;
 }
 
-// with_dR: also refresh the OpenCV dR/dr tables [C + M][27] the explicit-Jacobian / dense paths read
-int launch_prepare(pcs_problem* p, bool with_dR)
+// with_dR: also refresh the OpenCV dR/dr tables [C + M][27] the explicit-Jacobian / dense paths read.
+// x_dev / zero: see k_prepare_tables (one launch instead of scatter + tables + memset).
+int launch_prepare(pcs_problem* p, bool with_dR, const double* x_dev, double* zero, int64_t n_zero)
 {
     if (with_dR && !p->dRtab) PCS_TRY(dev_alloc(&p->dRtab, 27 * ((int64_t)p->C + p->M)));
-    k_prepare_tables<<<grid_for(p->C + p->M, 128), 128, 0, p->stream>>>(p->C, p->M, p->params, p->camtab, p->posetab,
-                                                                       with_dR ? p->dRtab : nullptr);
+    const int64_t n_tail = x_dev ? p->L - 15 * (int64_t)p->C - 6 * (int64_t)p->M : 0;
+    const int64_t threads = (int64_t)p->C + p->M + n_tail;
+    const int grid = (int)std::max<int64_t>(grid_for(threads, 128), std::min<int64_t>(grid_for(n_zero, 128), 2 * p->sm_count));
+    k_prepare_tables<<<grid, 128, 0, p->stream>>>(p->C, p->M, n_tail, p->params, x_dev, p->free_map, p->camtab, p->posetab,
+                                                  with_dR ? p->dRtab : nullptr, zero, zero ? n_zero : 0);
     ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;
@@ -788,9 +818,9 @@ int pcs_normal_equations_dev(pcs_problem* p, const double* x_dev)
         return PCS_ERR_UNSUPPORTED;
     }
     PCS_CUDA(cudaSetDevice(p->device));
-    if (x_dev) PCS_TRY(launch_scatter_x(p, x_dev));
-    PCS_TRY(launch_prepare(p));
-    return launch_normal_blocks(p);
+    // one launch: x -> parameter string, camera / pose tables, cleared reduction targets [U | gc | cost | pad | V | gp]
+    PCS_TRY(launch_prepare(p, false, x_dev, p->ne, (p->V - p->ne) + (int64_t)p->M * 42));
+    return launch_normal_blocks(p, true);
 }
 
 int pcs_normal_equations(pcs_problem* p, const double* x, double* U, double* gc, double* V, double* gp, double* W,

@@ -97,10 +97,11 @@ struct pcs_problem {
 namespace pcs {
 // kernels / launchers implemented in pcs_core.cu, used by pcs_solver.cu
 int launch_scatter_x(pcs_problem* p, const double* x_dev);
-int launch_prepare(pcs_problem* p, bool with_dR = false);
+int launch_prepare(pcs_problem* p, bool with_dR = false, const double* x_dev = nullptr, double* zero = nullptr,
+                   int64_t n_zero = 0);
 int launch_residual(pcs_problem* p, double* r_dev);
 int launch_cost_only(pcs_problem* p, double* cost_dev);
-int launch_normal_blocks(pcs_problem* p);
+int launch_normal_blocks(pcs_problem* p, bool targets_cleared = false);
 int ensure_pinned(pcs_problem* p, int64_t doubles);
 void lm_free(pcs_problem* p);
 }  // namespace pcs

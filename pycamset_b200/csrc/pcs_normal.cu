@@ -23,7 +23,8 @@
 //   * Two accumulator sets: the segment's (flushed per segment through a 2 KB shared scratch: W by coalesced plain
 //     stores -- the warp owns the segment -- V/g_m by FP64 reductions) and the camera's (U_c, g_c, r.r; flushed when
 //     the camera changes).
-//   * k_normal_epilogue applies the SO(3) left Jacobians once per block (tangent -> rvec parametrisation).
+//   * Rotation rows are accumulated in the tangent parametrisation; the SO(3) left Jacobians are applied once per
+//     block inside the flushes (Jl_m folded into the adjoint, Jl_c on three rows of W_s and on U_c / g_c).
 //   HBM traffic per observation: (u,v) 16 B + camera, pose, key 12 B = 28 B read; outputs are O(segments).
 #include <algorithm>
 #include <cstdlib>
@@ -35,7 +36,7 @@ namespace pcs {
 
 constexpr int NE_WARPS = 4;                  // warps per CTA
 constexpr int NE_TILE_DOUBLES = 64 * 8;      // one 8-column tile of the 64 staged rows
-constexpr int NE_SCRATCH_DOUBLES = 64;                 // Tbar (8 x 8), see flush_segment
+constexpr int NE_SCRATCH_DOUBLES = 64 + 256;           // Tbar (8 x 8, flush_segment) | camera block (16 x 16, flush_camera)
 constexpr int NE_WARP_DOUBLES = 2 * NE_TILE_DOUBLES + NE_SCRATCH_DOUBLES;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
@@ -102,7 +103,7 @@ __device__ __forceinline__ void tile_times_tbar(const double x[2], double tb0, d
 // on the FP64 tensor path:
 //     Wbar_A = ab Tbar, Wbar_B = bb Tbar   -> W_s[a][j] (a < 15, j < 6), final in the pose columns
 //     Vbar   = Tbar^T Wbar_B               -> V_m += Vbar[0:6,0:6], g_m += Vbar[0:6,6]
-// (rows 9..11 of W_s still need the camera's left Jacobian: k_normal_epilogue).
+// Rows 9..11 of W_s are then rotated from the camera's tangent frame with Jl_c (three shuffled rows).
 __device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int64_t seg, int c, int m,
                                               const double* __restrict__ camtab, const double* __restrict__ posetab,
                                               double* __restrict__ tbar, double* __restrict__ V, double* __restrict__ gp,
@@ -143,6 +144,18 @@ __device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int6
         dmma884(vb[0], vb[1], tb1, b1);
     }
     const int row = lane >> 2, cp = 2 * (lane & 3);
+    {   // rows 9..11 of W_s (rows 1..3 of Wbar_B) are in the camera's tangent frame: new row i = sum_i' Jl_c[i'][i] row i'
+        const int q = lane & 3;
+        const double x10 = __shfl_sync(0xffffffffu, wb[0], 4 + q), x11 = __shfl_sync(0xffffffffu, wb[1], 4 + q);
+        const double x20 = __shfl_sync(0xffffffffu, wb[0], 8 + q), x21 = __shfl_sync(0xffffffffu, wb[1], 8 + q);
+        const double x30 = __shfl_sync(0xffffffffu, wb[0], 12 + q), x31 = __shfl_sync(0xffffffffu, wb[1], 12 + q);
+        if (row >= 1 && row <= 3) {
+            const double* jl = camtab + (int64_t)c * CAM_STRIDE + CAM_JL + (row - 1);
+            const double j0 = jl[0], j1 = jl[3], j2 = jl[6];
+            wb[0] = x10 * j0 + x20 * j1 + x30 * j2;
+            wb[1] = x11 * j0 + x21 * j1 + x31 * j2;
+        }
+    }
     if (cp < 6) {   // W_s[a][cp], W_s[a][cp + 1]: 16-byte stores
         double* Ws = W + seg * 90 + cp;
         *reinterpret_cast<double2*>(Ws + row * 6) = make_double2(wa[0], wa[1]);
@@ -157,28 +170,64 @@ __device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int6
     acc_zero(S);
 }
 
-// Camera flush: U_c (both triangles), g_c and r.r from the running camera sums
-__device__ __forceinline__ void flush_camera(NeAcc& C, int lane, int c, double* __restrict__ U, double* __restrict__ gc,
+// Camera flush: the running camera sums (tangent parametrisation) go through a 16 x 16 shared scratch, are mapped
+// to the reference's rvec parametrisation, B = T^T B' T with T = diag(I9, Jl_c, I3, 1), and are added to U_c
+// (both triangles), g_c and r.r with FP64 reductions.  Runs once per (warp, camera): cost is irrelevant.
+__device__ __forceinline__ void flush_camera(NeAcc& C, int lane, int c, const double* __restrict__ camtab,
+                                             double* __restrict__ G, double* __restrict__ U, double* __restrict__ gc,
                                              double* __restrict__ cost)
 {
     const int row = lane >> 2, cp = 2 * (lane & 3);
-    double* Uc = U + (int64_t)c * 225;
-    double* gcc = gc + (int64_t)c * 15;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int col = cp + i;
-        atomicAdd(Uc + row * 15 + col, C.aa[i]);
-        if (col < 7) {
-            atomicAdd(Uc + row * 15 + 8 + col, C.ab[i]);
-            atomicAdd(Uc + (8 + col) * 15 + row, C.ab[i]);
-            if (row < 7) atomicAdd(Uc + (8 + row) * 15 + 8 + col, C.bb[i]);
-        } else {
-            atomicAdd(gcc + row, C.ab[i]);
-            if (row < 7) atomicAdd(gcc + 8 + row, C.bb[i]);
-            else atomicAdd(cost, C.bb[i]);
-        }
+        G[row * 16 + col] = C.aa[i];
+        G[row * 16 + 8 + col] = C.ab[i];
+        G[(8 + col) * 16 + row] = C.ab[i];
+        G[(8 + row) * 16 + 8 + col] = C.bb[i];
     }
     acc_zero(C);
+    const double* jl = camtab + (int64_t)c * CAM_STRIDE + CAM_JL;
+    const double j[9] = {jl[0], jl[1], jl[2], jl[3], jl[4], jl[5], jl[6], jl[7], jl[8]};
+    __syncwarp();
+    if (lane < 16) {  // columns 9..11 of row `lane`  <-  row * Jl
+        const double a0 = G[lane * 16 + 9], a1 = G[lane * 16 + 10], a2 = G[lane * 16 + 11];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) G[lane * 16 + 9 + i] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
+    }
+    __syncwarp();
+    if (lane < 16) {  // rows 9..11 of column `lane`  <-  Jl^T * column
+        const double a0 = G[9 * 16 + lane], a1 = G[10 * 16 + lane], a2 = G[11 * 16 + lane];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) G[(9 + i) * 16 + lane] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
+    }
+    __syncwarp();
+    double* Uc = U + (int64_t)c * 225;
+    for (int e = lane; e < 225; e += 32) {
+        const int a = e / 15, b = e - 15 * a;
+        atomicAdd(Uc + e, G[a * 16 + b]);
+    }
+    if (lane < 15) atomicAdd(gc + (int64_t)c * 15 + lane, G[lane * 16 + 15]);
+    if (lane == 15) atomicAdd(cost, G[15 * 16 + 15]);
+    __syncwarp();
+}
+
+// One k-step (2 observations = 4 staged rows) of the Gram update.  MASKED: rows of observations outside [a, b)
+// (a neighbouring piece sharing the step, or stale rows past the batch) contribute zero.
+template <bool MASKED>
+__device__ __forceinline__ void gram_step(NeAcc& S, const double* __restrict__ ws, int ld_L, int ks, int jb, int a, int b)
+{
+    const double* f = ws + 32 * ks + (ld_L ^ (((ks & 1) << 3) | (ks & 2)));
+    double v0 = f[0], v1 = f[NE_TILE_DOUBLES];
+    if (MASKED) {
+        const int ob = 2 * ks + jb;
+        const bool ok = ob >= a && ob < b;
+        v0 = ok ? v0 : 0.0;
+        v1 = ok ? v1 : 0.0;
+    }
+    dmma884(S.aa[0], S.aa[1], v0, v0);
+    dmma884(S.ab[0], S.ab[1], v0, v1);
+    dmma884(S.bb[0], S.bb[1], v1, v1);
 }
 
 template <int CTAS_PER_SM>
@@ -252,6 +301,12 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
                 stage_store_row(st_v, st_rot, t0, t1);
             }
         }
+        // the next batch's pose row (new for every segment) is pulled into L1 while this batch's Gram phase runs
+        if (m_n >= 0) {
+            const double* nx = posetab + (int64_t)m_n * POSE_STRIDE;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
+        }
         // piece heads: lanes whose (camera, pose) differs from the previous observation's
         int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
         if (lane == 0) { pc = last_c; pm = last_m; }
@@ -267,28 +322,41 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
             if ((heads >> a) & 1u) {
                 if (cur_c >= 0) flush_segment(S, C, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, V, gp, W);
                 const int nc = __shfl_sync(0xffffffffu, c, a);
-                if (nc != cur_c && cur_c >= 0) flush_camera(C, lane, cur_c, U, gc, cost);
+                if (nc != cur_c && cur_c >= 0) flush_camera(C, lane, cur_c, camtab, scratch + 64, U, gc, cost);
                 ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
             }
-            const int k0 = a >> 1, k1 = (b - 1) >> 1;
-            for (int ks = k0; ks <= k1; ++ks) {
-                const double* f = ws + 32 * ks + (ld_L ^ (((ks & 1) << 3) | (ks & 2)));
-                double v0 = f[0], v1 = f[NE_TILE_DOUBLES];
-                if (ks == k0 || ks == k1) {  // boundary k-steps may hold rows of a neighbouring segment (or stale rows)
-                    const int ob = 2 * ks + jb;
-                    const bool ok = ob >= a && ob < b;
-                    v0 = ok ? v0 : 0.0; v1 = ok ? v1 : 0.0;
-                }
-                dmma884(S.aa[0], S.aa[1], v0, v0);
-                dmma884(S.ab[0], S.ab[1], v0, v1);
-                dmma884(S.bb[0], S.bb[1], v1, v1);
+            // k-steps of the piece: boundary steps shared with a neighbouring piece (odd a / odd b) are masked,
+            // interior steps run unmasked in groups of four with their fragment loads hoisted
+            int ks = a >> 1;
+            const int k1 = (b - 1) >> 1;
+            if (a & 1) {
+                gram_step<true>(S, ws, ld_L, ks, jb, a, b);
+                ++ks;
             }
+            const int k_full = (b & 1) ? k1 : k1 + 1;   // first step that needs the tail mask (or one past the end)
+            for (; ks + 4 <= k_full; ks += 4) {
+                double v0[4], v1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double* f = ws + 32 * (ks + u) + (ld_L ^ ((((ks + u) & 1) << 3) | ((ks + u) & 2)));
+                    v0[u] = f[0];
+                    v1[u] = f[NE_TILE_DOUBLES];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    dmma884(S.aa[0], S.aa[1], v0[u], v0[u]);
+                    dmma884(S.ab[0], S.ab[1], v0[u], v1[u]);
+                    dmma884(S.bb[0], S.bb[1], v1[u], v1[u]);
+                }
+            }
+            for (; ks < k_full; ++ks) gram_step<false>(S, ws, ld_L, ks, jb, a, b);
+            if (ks <= k1) gram_step<true>(S, ws, ld_L, ks, jb, a, b);
         }
         __syncwarp();
     }
     if (cur_c >= 0) {
         flush_segment(S, C, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, V, gp, W);
-        flush_camera(C, lane, cur_c, U, gc, cost);
+        flush_camera(C, lane, cur_c, camtab, scratch + 64, U, gc, cost);
     }
 }
 
@@ -305,55 +373,6 @@ __global__ void k_warp_ranges(int64_t N, int64_t n_seg, int n_warps, const int64
     warp_seg[w] = w == n_warps ? n_seg : lo;
 }
 
-// Epilogue: the camera-rotation rows / columns are accumulated in the tangent parametrisation; this maps them to the
-// reference's rvec parametrisation with the camera's left Jacobian, B = T^T B' T, T_c = diag(I9, Jl_c, I3).
-// (The pose side is final already: flush_segment folds Jl_m into the adjoint.)
-//   blocks [0, C)   : U_c, g_c            (one block of 64 threads per camera)
-//   blocks [C, ...) : rows 9..11 of W_s   (6 threads per segment: one per pose column; 144 contiguous bytes)
-__global__ void __launch_bounds__(64)
-k_normal_epilogue(int C, int64_t n_seg, const int32_t* __restrict__ seg_cam, const double* __restrict__ camtab,
-                  double* __restrict__ U, double* __restrict__ gc, double* __restrict__ W)
-{
-    const int t = threadIdx.x;
-    if ((int)blockIdx.x < C) {
-        const int c = blockIdx.x;
-        __shared__ double u[225];
-        __shared__ double jl[9];
-        double* Uc = U + (int64_t)c * 225;
-        for (int e = t; e < 225; e += 64) u[e] = Uc[e];
-        if (t < 9) jl[t] = camtab[(int64_t)c * CAM_STRIDE + CAM_JL + t];
-        __syncthreads();
-        if (t < 15) {  // columns 9..11 of row t  <-  row * Jl
-            const double a0 = u[t * 15 + 9], a1 = u[t * 15 + 10], a2 = u[t * 15 + 11];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) u[t * 15 + 9 + i] = a0 * jl[i] + a1 * jl[3 + i] + a2 * jl[6 + i];
-        } else if (t == 15) {  // g_c[9..11] <- Jl^T g
-            double* g = gc + (int64_t)c * 15 + 9;
-            const double a0 = g[0], a1 = g[1], a2 = g[2];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) g[i] = a0 * jl[i] + a1 * jl[3 + i] + a2 * jl[6 + i];
-        }
-        __syncthreads();
-        if (t < 15) {  // rows 9..11 of column t  <-  Jl^T * column
-            const double a0 = u[9 * 15 + t], a1 = u[10 * 15 + t], a2 = u[11 * 15 + t];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) u[(9 + i) * 15 + t] = a0 * jl[i] + a1 * jl[3 + i] + a2 * jl[6 + i];
-        }
-        __syncthreads();
-        for (int e = t; e < 225; e += 64) Uc[e] = u[e];
-        return;
-    }
-    const int64_t idx = ((int64_t)blockIdx.x - C) * 64 + t;
-    const int64_t s = idx / 6;
-    if (s >= n_seg) return;
-    const int j = (int)(idx - 6 * s);
-    const double* jl = camtab + (int64_t)seg_cam[s] * CAM_STRIDE + CAM_JL;
-    double* w = W + s * 90 + 54 + j;   // rows 9, 10, 11 of column j
-    const double a0 = w[0], a1 = w[6], a2 = w[12];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) w[6 * i] = a0 * jl[i] + a1 * jl[3 + i] + a2 * jl[6 + i];
-}
-
 static int ensure_ranges(pcs_problem* p, int64_t n_ranges)
 {
     if (p->ne_warps == n_ranges) return PCS_OK;
@@ -367,11 +386,13 @@ static int ensure_ranges(pcs_problem* p, int64_t n_ranges)
     return PCS_OK;
 }
 
-int launch_normal_blocks(pcs_problem* p)
+int launch_normal_blocks(pcs_problem* p, bool targets_cleared)
 {
     // zero what is accumulated with reductions: [U | gc | cost | pad | V | gp]; W is fully overwritten
-    const int64_t zero_doubles = (p->V - p->ne) + (int64_t)p->M * 42;
-    PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
+    if (!targets_cleared) {
+        const int64_t zero_doubles = (p->V - p->ne) + (int64_t)p->M * 42;
+        PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
+    }
     if (p->N == 0) return PCS_OK;
     // resident CTAs per SM: 4 x 128 registers (default) or 3 x 154; PCS_NE_CTAS=3 selects the latter for A/B runs
     static const int ctas = [] { const char* e = std::getenv("PCS_NE_CTAS"); return e && e[0] >= '3' && e[0] <= '5' ? e[0] - '0' : 4; }();
@@ -392,11 +413,7 @@ int launch_normal_blocks(pcs_problem* p)
                                                   (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab, p->tmpl,
                                                   p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
-    const int64_t w_blocks = (p->n_seg * 6 + 63) / 64;
-    k_normal_epilogue<<<(unsigned)(p->C + w_blocks), 64, 0, p->stream>>>(p->C, p->n_seg, p->seg_cam, p->camtab, p->U, p->gc,
-                                                                        p->W);
-    PCS_CUDA(cudaGetLastError());
-    p->n_launches += 2;
+    ++p->n_launches;
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_b, p->stream));
     return PCS_OK;
 }
