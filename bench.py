@@ -261,6 +261,7 @@ def main():
     ap.add_argument("--no-lm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lm-iters", type=int, default=10)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: camera-block all-reduce path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -298,10 +299,40 @@ def main():
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
 
+    # N > 1: the one exchange step of the pose-sharded evaluation is the sum of the camera blocks [U | gc | cost].
+    # Default: the library's one-shot all-reduce over NVLink peer memory (csrc/pcs_p2p.cu); --exchange nccl uses
+    # torch.distributed (NCCL) instead.  The peer-memory path is checked against NCCL once before timing.
+    exchange, exchange_check = None, None
+    if world > 1:
+        exchange = "nccl"
+        if args.exchange == "p2p":
+            try:
+                p2p = pdist.P2PCameraAllReduce(prob)
+                n_head = prob.n_cams * 240 + 1
+                head = pdist.tensor_from_ptr(prob.device_buffers().U, n_head, dev)
+                with torch.cuda.stream(stream):
+                    prob.normal_equations_device(x_dev.data_ptr())
+                    ref = head.clone()
+                    dist.all_reduce(ref)
+                    p2p()
+                    err = float(((head - ref).abs().max() / ref.abs().max()).item())
+                    p2p()   # second call exercises the other data slot (result: world * sum; only the protocol matters)
+                torch.cuda.synchronize(dev)
+                ok = torch.tensor([1.0 if err < 1e-12 else 0.0], device=f"cuda:{dev}")
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if ok.item() < 1.0:
+                    raise RuntimeError(f"peer-memory all-reduce disagrees with NCCL (rel err {err:.3e})")
+                exchange, exchange_check = "p2p", f"matches NCCL all-reduce, rel err {err:.1e}"
+            except Exception as e:  # symmetric memory unavailable on this box: say so and use NCCL
+                exchange, exchange_check = "nccl", f"p2p unavailable: {str(e)[:160]}"
+
     def step():
         prob.normal_equations_device(x_dev.data_ptr())
         if world > 1:
-            pdist.allreduce_camera_blocks(prob)
+            if exchange == "p2p":
+                p2p()
+            else:
+                pdist.allreduce_camera_blocks(prob)
 
     def barrier():
         if world > 1:
@@ -328,11 +359,11 @@ def main():
             starts[k].record(stream)
             step()
             ends[k].record(stream)
-            kern_ms.append(prob.timing_normal_kernel_ms())
         barrier()
         wall_s = time.perf_counter() - t_wall
         gpu_launches = prob.launch_count() - launches0
         clocks = sampler.stop() if rank == 0 else None
+        kern_ms = prob.timing_all_ms()[-args.steps:]   # per-launch event pairs recorded by the library, read after the loop
         prob.timing_enable(False)
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(np.sum(step_ms))
@@ -418,7 +449,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mobs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": sh["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {**workload_config(args, sh, world), "n_obs_total": n_total, "n_obs_per_gpu": n_local,
+            "config": {**workload_config(args, sh, world), "exchange": exchange, "exchange_check": exchange_check,
+                       "n_obs_total": n_total, "n_obs_per_gpu": n_local,
                        "n_segments_per_gpu": prob.n_segments, "n_free_per_gpu": prob.n_free},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "normal-equation kernel (K_ne)",

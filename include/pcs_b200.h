@@ -151,6 +151,16 @@ PCS_API int pcs_device_buffers_get(pcs_problem* p, pcs_device_buffers* out);
 typedef int (*pcs_allreduce_fn)(void* user, double* buf_dev, int64_t n, int op, void* stream);
 PCS_API int pcs_set_allreduce(pcs_problem* p, pcs_allreduce_fn fn, void* user, int rank, int world_size);
 
+/* Multi-GPU, raw evaluation: one-shot all-reduce (sum, rank order) of the camera blocks [U | gc | cost] over NVLink
+ * peer memory -- the only exchange step of a pose-sharded normal-equation evaluation (C * 240 + 1 doubles, latency
+ * bound).  Every rank allocates a zero-initialised buffer of pcs_p2p_buffer_bytes(p, world) that all peers have mapped
+ * (e.g. torch.distributed._symmetric_memory) and passes the world's pointers, own buffer at index `rank`.
+ * pcs_p2p_allreduce_camera_blocks enqueues one single-CTA kernel on the problem's stream; all ranks must call it the
+ * same number of times.  No reference counterpart (the reference is single-process). */
+PCS_API int64_t pcs_p2p_buffer_bytes(const pcs_problem* p, int world_size);
+PCS_API int pcs_p2p_allreduce_setup(pcs_problem* p, int rank, int world_size, void* const* peer_buffers, int64_t buffer_bytes);
+PCS_API int pcs_p2p_allreduce_camera_blocks(pcs_problem* p);
+
 /* Levenberg-Marquardt on the device (replaces scipy.optimize.least_squares TRF + LSMR as driven by
  * run_bundle_adjustment, optimisation_handling.py:52-117). */
 typedef struct pcs_lm_options {
@@ -176,10 +186,13 @@ PCS_API void pcs_lm_default_options(pcs_lm_options* o);
 PCS_API int pcs_lm_solve(pcs_problem* p, const double* x0 /*[n_free]*/, const pcs_lm_options* opts,
                          double* x_out /*[n_free]*/, pcs_lm_stats* stats);
 
-/* Optional kernel timing: when enabled, the fused normal-equation kernel is bracketed by CUDA events on the
- * problem's stream; pcs_timing_get returns the duration (ms) of its most recent launch (synchronises). */
+/* Optional kernel timing: when enabled, every launch of the fused normal-equation kernel is bracketed by a pair of
+ * CUDA events on the problem's stream (a ring of 1024 pairs, so a timed loop needs no synchronisation inside).
+ * pcs_timing_get returns the duration (ms) of the most recent launch, pcs_timing_get_all the durations of the last
+ * launches since timing was enabled, oldest first (both synchronise on the events they read). */
 PCS_API int pcs_timing_enable(pcs_problem* p, int on);
 PCS_API int pcs_timing_get(pcs_problem* p, double* normal_kernel_ms);
+PCS_API int pcs_timing_get_all(pcs_problem* p, double* ms, int64_t capacity, int64_t* n_out);
 
 /* Number of kernels of this library launched so far for the residual / Jacobian / normal-equation evaluations of
  * this problem (cuBLAS / cuSOLVER launches inside pcs_lm_solve are not counted).  bench.py reports the difference

@@ -20,8 +20,8 @@ EXPORTED_SYMBOLS = [
     "pcs_set_param_string", "pcs_set_free", "pcs_get_param_string", "pcs_residual", "pcs_residual_dev",
     "pcs_csr_structure", "pcs_jacobian_values", "pcs_jacobian_values_dev", "pcs_segments", "pcs_normal_equations",
     "pcs_normal_equations_dev", "pcs_normal_dense", "pcs_device_buffers_get", "pcs_set_allreduce",
-    "pcs_lm_default_options", "pcs_lm_solve", "pcs_timing_enable", "pcs_timing_get", "pcs_launch_count",
-    "pcs_device_sm_count",
+    "pcs_lm_default_options", "pcs_lm_solve", "pcs_timing_enable", "pcs_timing_get", "pcs_timing_get_all", "pcs_launch_count",
+    "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_device_sm_count",
     "pcs_version",
 ]
 
@@ -112,7 +112,12 @@ def load() -> ct.CDLL:
     lib.pcs_lm_solve.argtypes = [vp, vp, ct.POINTER(LmOptions), vp, ct.POINTER(LmStats)]
     lib.pcs_timing_enable.argtypes = [vp, ct.c_int]
     lib.pcs_timing_get.argtypes = [vp, ct.POINTER(ct.c_double)]
+    lib.pcs_timing_get_all.argtypes = [vp, vp, ct.c_int64, ct.POINTER(ct.c_int64)]
     lib.pcs_launch_count.argtypes = [vp, ct.POINTER(ct.c_int64)]
+    lib.pcs_p2p_buffer_bytes.argtypes = [vp, ct.c_int]
+    lib.pcs_p2p_buffer_bytes.restype = ct.c_int64
+    lib.pcs_p2p_allreduce_setup.argtypes = [vp, ct.c_int, ct.c_int, ct.POINTER(vp), ct.c_int64]
+    lib.pcs_p2p_allreduce_camera_blocks.argtypes = [vp]
     lib.pcs_device_sm_count.argtypes = [ct.c_int]
     _lib = lib
     return lib

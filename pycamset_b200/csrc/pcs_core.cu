@@ -456,14 +456,15 @@ int pcs_problem_destroy(pcs_problem* p)
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     lm_free(p);
+    p2p_free(p);
     dev_free(p->cam); dev_free(p->pose); dev_free(p->key); dev_free(p->uv); dev_free(p->tmpl);
     dev_free(p->free_map); dev_free(p->free_idx); dev_free(p->cam_mask); dev_free(p->pose_mask); dev_free(p->key_mask);
     dev_free(p->row_prefix); dev_free(p->params); dev_free(p->x); dev_free(p->camtab); dev_free(p->posetab);
     dev_free(p->resid); dev_free(p->jvals); dev_free(p->seg_cam); dev_free(p->seg_pose); dev_free(p->seg_start);
     dev_free(p->s_key); dev_free(p->s_cam); dev_free(p->s_pose); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense); dev_free(p->warp_seg); dev_free(p->dRtab);
     if (p->h_pin) cudaFreeHost(p->h_pin);
-    if (p->ev_a) cudaEventDestroy(p->ev_a);
-    if (p->ev_b) cudaEventDestroy(p->ev_b);
+    for (cudaEvent_t e : p->ev_a) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->ev_b) cudaEventDestroy(e);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return PCS_OK;
@@ -900,26 +901,52 @@ int pcs_launch_count(const pcs_problem* p, int64_t* n_kernels)
     return PCS_OK;
 }
 
+constexpr int TIMING_RING = 1024;
+
 int pcs_timing_enable(pcs_problem* p, int on)
 {
     PCS_REQUIRE(p, "NULL argument");
     PCS_CUDA(cudaSetDevice(p->device));
-    if (on && !p->ev_a) {
-        PCS_CUDA(cudaEventCreate(&p->ev_a));
-        PCS_CUDA(cudaEventCreate(&p->ev_b));
+    if (on && p->ev_a.empty()) {
+        p->ev_a.resize(TIMING_RING);
+        p->ev_b.resize(TIMING_RING);
+        for (int i = 0; i < TIMING_RING; ++i) {
+            PCS_CUDA(cudaEventCreate(&p->ev_a[i]));
+            PCS_CUDA(cudaEventCreate(&p->ev_b[i]));
+        }
     }
+    if (on) p->timing_count = 0;
     p->timing = on != 0;
     return PCS_OK;
 }
 
+// most recent launch
 int pcs_timing_get(pcs_problem* p, double* ms)
 {
-    PCS_REQUIRE(p && ms && p->ev_a, "timing was never enabled");
+    PCS_REQUIRE(p && ms && !p->ev_a.empty() && p->timing_count > 0, "no timed launch recorded");
     PCS_CUDA(cudaSetDevice(p->device));
-    PCS_CUDA(cudaEventSynchronize(p->ev_b));
+    const int i = (int)((p->timing_count - 1) % TIMING_RING);
+    PCS_CUDA(cudaEventSynchronize(p->ev_b[i]));
     float f = 0.f;
-    PCS_CUDA(cudaEventElapsedTime(&f, p->ev_a, p->ev_b));
+    PCS_CUDA(cudaEventElapsedTime(&f, p->ev_a[i], p->ev_b[i]));
     *ms = f;
+    return PCS_OK;
+}
+
+// durations (ms) of the last min(count, capacity, ring) launches since pcs_timing_enable(p, 1), oldest first
+int pcs_timing_get_all(pcs_problem* p, double* ms, int64_t capacity, int64_t* n_out)
+{
+    PCS_REQUIRE(p && ms && n_out && !p->ev_a.empty(), "timing was never enabled");
+    PCS_CUDA(cudaSetDevice(p->device));
+    const int64_t n = std::min<int64_t>(std::min<int64_t>(p->timing_count, TIMING_RING), capacity);
+    for (int64_t k = 0; k < n; ++k) {
+        const int i = (int)((p->timing_count - n + k) % TIMING_RING);
+        PCS_CUDA(cudaEventSynchronize(p->ev_b[i]));
+        float f = 0.f;
+        PCS_CUDA(cudaEventElapsedTime(&f, p->ev_a[i], p->ev_b[i]));
+        ms[k] = f;
+    }
+    *n_out = n;
     return PCS_OK;
 }
 

@@ -83,12 +83,17 @@ struct pcs_problem {
     int rank = 0, world = 1;
 
     // optional event timing of the normal-equation kernel
+    // ring of (start, stop) event pairs, one per launch, read back without synchronising inside a timed loop
     bool timing = false;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    std::vector<cudaEvent_t> ev_a, ev_b;
+    int64_t timing_count = 0;   // launches recorded since timing was enabled
 
     int64_t* warp_seg = nullptr;  // [ne_warps + 1] segment range of every warp of the normal-equation kernel
     int64_t ne_warps = 0;
     int64_t n_launches = 0;  // kernels launched by this library on behalf of the problem (pcs_launch_count)
+
+    // peer-memory all-reduce state (pcs_p2p.cu)
+    void* p2p = nullptr;
 
     // LM workspace (pcs_solver.cu)
     void* lm_ws = nullptr;
@@ -104,4 +109,5 @@ int launch_cost_only(pcs_problem* p, double* cost_dev);
 int launch_normal_blocks(pcs_problem* p, bool targets_cleared = false);
 int ensure_pinned(pcs_problem* p, int64_t doubles);
 void lm_free(pcs_problem* p);
+void p2p_free(pcs_problem* p);
 }  // namespace pcs

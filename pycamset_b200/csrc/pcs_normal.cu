@@ -408,13 +408,17 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared)
     n_warps = std::max<int64_t>(1, std::min<int64_t>(n_warps, p->n_seg));
     PCS_TRY(ensure_ranges(p, n_warps));
     const int grid = (int)((n_warps + NE_WARPS - 1) / NE_WARPS);
-    if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a, p->stream));
+    const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
+    if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
     kern<<<grid, NE_WARPS * 32, smem, p->stream>>>((int)n_warps, p->warp_seg, p->s_cam, p->s_pose, p->s_key,
                                                   (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab, p->tmpl,
                                                   p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
     ++p->n_launches;
-    if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_b, p->stream));
+    if (p->timing) {
+        PCS_CUDA(cudaEventRecord(p->ev_b[tslot], p->stream));
+        ++p->timing_count;
+    }
     return PCS_OK;
 }
 

@@ -1,0 +1,131 @@
+// pcs_p2p.cu -- one-shot all-reduce of the camera blocks [U | g_c | r.r] over NVLink peer memory.
+//
+// The per-evaluation exchange of the pose-sharded problem is C * 240 + 1 doubles (61 KB at C = 32):
+// a latency problem, not a bandwidth one.  Every rank owns a "symmetric" buffer that all peers have mapped (the
+// Python host allocates it with torch's symmetric-memory allocator and passes the peer pointers in).  One CTA per
+// rank: write the local block into every peer's buffer (posted NVLink stores), raise a flag at every peer, wait for
+// every peer's flag, then add up the received blocks from local memory in rank order (bitwise identical result on
+// every rank).  Two data slots alternate so that a rank that races ahead never overwrites a block still being read.
+#include "pcs_internal.cuh"
+
+namespace pcs {
+
+constexpr int P2P_MAX_WORLD = 16;
+constexpr int64_t P2P_FLAG_DOUBLES = 32;   // 16 x uint64 flags, padded to 256 bytes
+
+struct P2PPeers {
+    double* buf[P2P_MAX_WORLD];
+};
+
+struct P2PState {
+    P2PPeers peers;
+    int rank = 0, world = 1;
+    int64_t n = 0;          // doubles exchanged
+    uint64_t epoch = 0;
+};
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Push protocol: every rank WRITES its block into slot [rank] of every peer's buffer (posted NVLink stores, no read
+// round trip), fences, raises its flag at every peer, waits for all flags in its own buffer and sums the `world`
+// slots it received from local memory.  Buffer layout per rank: flags | slot 0: [world][n] | slot 1: [world][n].
+template <int WORLD>
+__global__ void __launch_bounds__(1024)
+k_p2p_allreduce(double* __restrict__ local, int64_t n, int rank, int world_rt, P2PPeers peers, uint64_t epoch)
+{
+    const int world = WORLD > 0 ? WORLD : world_rt;
+    const int tid = threadIdx.x;
+    const int64_t data = P2P_FLAG_DOUBLES + (int64_t)(epoch & 1) * world * n;
+    for (int64_t i = tid; i < n; i += blockDim.x) {
+        const double v = local[i];
+#pragma unroll
+        for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+            if (r < world) peers.buf[r][data + (int64_t)rank * n + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    double* mine = peers.buf[rank];
+    if (tid < world) {
+        st_release_sys(reinterpret_cast<uint64_t*>(peers.buf[tid]) + rank, epoch);       // my flag in peer tid's buffer
+        const uint64_t* theirs = reinterpret_cast<const uint64_t*>(mine) + tid;           // peer tid's flag in mine
+        while (ld_acquire_sys(theirs) < epoch) { }
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+            if (r < world) s += ld_relaxed_sys(mine + data + (int64_t)r * n + i);   // rank order: identical bits everywhere
+        local[i] = s;
+    }
+}
+
+}  // namespace pcs
+
+using namespace pcs;
+
+extern "C" {
+
+int64_t pcs_p2p_buffer_bytes(const pcs_problem* p, int world)
+{
+    if (!p || world < 1) return 0;
+    const int64_t n = (int64_t)p->C * 240 + 1;
+    return (P2P_FLAG_DOUBLES + 2 * (int64_t)world * n) * (int64_t)sizeof(double);
+}
+
+int pcs_p2p_allreduce_setup(pcs_problem* p, int rank, int world, void* const* peer_buffers, int64_t buffer_bytes)
+{
+    PCS_REQUIRE(p && peer_buffers, "NULL argument");
+    PCS_REQUIRE(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "rank / world out of range");
+    PCS_REQUIRE(buffer_bytes >= pcs_p2p_buffer_bytes(p, world), "symmetric buffer is smaller than pcs_p2p_buffer_bytes()");
+    P2PState* st = (P2PState*)p->p2p;
+    if (!st) {
+        st = new P2PState();
+        p->p2p = st;
+    }
+    for (int r = 0; r < world; ++r) {
+        PCS_REQUIRE(peer_buffers[r], "peer buffer pointer is NULL");
+        st->peers.buf[r] = (double*)peer_buffers[r];
+    }
+    st->rank = rank; st->world = world; st->n = (int64_t)p->C * 240 + 1; st->epoch = 0;
+    return PCS_OK;
+}
+
+int pcs_p2p_allreduce_camera_blocks(pcs_problem* p)
+{
+    PCS_REQUIRE(p && p->p2p, "pcs_p2p_allreduce_setup has not been called");
+    PCS_CUDA(cudaSetDevice(p->device));
+    P2PState* st = (P2PState*)p->p2p;
+    ++st->epoch;
+    auto kern = st->world == 2 ? k_p2p_allreduce<2> : st->world == 4 ? k_p2p_allreduce<4> : st->world == 8 ? k_p2p_allreduce<8>
+                                                                                                          : k_p2p_allreduce<0>;
+    kern<<<1, 1024, 0, p->stream>>>(p->U, st->n, st->rank, st->world, st->peers, st->epoch);
+    PCS_CUDA(cudaGetLastError());
+    ++p->n_launches;
+    return PCS_OK;
+}
+
+}  // extern "C"
+
+namespace pcs {
+void p2p_free(pcs_problem* p)
+{
+    delete (P2PState*)p->p2p;
+    p->p2p = nullptr;
+}
+}  // namespace pcs

@@ -96,3 +96,28 @@ def allreduce_camera_blocks(problem, group=None):
     with torch.cuda.stream(ext):
         dist.all_reduce(t, group=group)
     return t
+
+
+class P2PCameraAllReduce:
+    """Low-latency replacement for `allreduce_camera_blocks`: the camera blocks are exchanged by one single-CTA kernel
+    over NVLink peer memory (csrc/pcs_p2p.cu).  torch's symmetric-memory allocator only provides the plumbing: a
+    buffer per rank that every peer has mapped."""
+
+    def __init__(self, problem, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        self.problem = problem
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = problem.p2p_buffer_bytes(self.world)
+        self.buf = symm_mem.empty(nbytes // 8, dtype=torch.float64, device=f"cuda:{problem.device}")
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group.group_name)
+        torch.cuda.synchronize(problem.device)
+        dist.barrier(group)                       # every rank's flags are zero before anyone starts signalling
+        problem.p2p_setup(self.rank, self.world, list(self.handle.buffer_ptrs), nbytes)
+
+    def __call__(self):
+        self.problem.p2p_allreduce_camera_blocks()

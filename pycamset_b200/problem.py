@@ -220,10 +220,27 @@ class BundleProblem:
         L.check(self._lib.pcs_timing_get(self._h, ct.byref(ms)))
         return ms.value
 
+    def timing_all_ms(self, capacity=1024) -> np.ndarray:
+        """Durations (ms) of the normal-equation kernel launches since timing_enable(True), oldest first."""
+        out = np.empty(capacity)
+        n = ct.c_int64()
+        L.check(self._lib.pcs_timing_get_all(self._h, _ptr(out), capacity, ct.byref(n)))
+        return out[:n.value].copy()
+
     def launch_count(self) -> int:
         n = ct.c_int64()
         L.check(self._lib.pcs_launch_count(self._h, ct.byref(n)))
         return n.value
+
+    def p2p_buffer_bytes(self, world_size) -> int:
+        return int(self._lib.pcs_p2p_buffer_bytes(self._h, int(world_size)))
+
+    def p2p_setup(self, rank, world_size, peer_ptrs, buffer_bytes):
+        arr = (ct.c_void_p * world_size)(*[ct.c_void_p(int(q)) for q in peer_ptrs])
+        L.check(self._lib.pcs_p2p_allreduce_setup(self._h, int(rank), int(world_size), arr, int(buffer_bytes)))
+
+    def p2p_allreduce_camera_blocks(self):
+        L.check(self._lib.pcs_p2p_allreduce_camera_blocks(self._h))
 
     def set_allreduce(self, fn, rank, world_size):
         """fn(ptr:int, n:int, op:int, stream:int) -> None; installed as the multi-GPU combine hook of the LM solver."""
