@@ -461,10 +461,13 @@ int pcs_problem_destroy(pcs_problem* p)
     dev_free(p->free_map); dev_free(p->free_idx); dev_free(p->cam_mask); dev_free(p->pose_mask); dev_free(p->key_mask);
     dev_free(p->row_prefix); dev_free(p->params); dev_free(p->x); dev_free(p->camtab); dev_free(p->posetab);
     dev_free(p->resid); dev_free(p->jvals); dev_free(p->seg_cam); dev_free(p->seg_pose); dev_free(p->seg_start);
-    dev_free(p->s_key); dev_free(p->s_cam); dev_free(p->s_pose); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense); dev_free(p->warp_seg); dev_free(p->dRtab);
+    dev_free(p->s_key); dev_free(p->s_cam); dev_free(p->s_pose); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense); dev_free(p->warp_seg[0]); dev_free(p->warp_seg[1]); dev_free(p->dRtab);
     if (p->h_pin) cudaFreeHost(p->h_pin);
     for (cudaEvent_t e : p->ev_a) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_b) cudaEventDestroy(e);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (cudaEvent_t e : p->part_done) if (e) cudaEventDestroy(e);
+    if (p->copy_done) cudaEventDestroy(p->copy_done);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return PCS_OK;
@@ -828,16 +831,50 @@ int pcs_normal_equations(pcs_problem* p, const double* x, double* U, double* gc,
                          double* cost)
 {
     PCS_REQUIRE(p, "NULL argument");
+    if (p->chain != PCS_CHAIN_TEMPLATE) {
+        set_error("block normal equations are implemented for the template chain; use pcs_normal_dense for the self-calibration chain");
+        return PCS_ERR_UNSUPPORTED;
+    }
     PCS_CUDA(cudaSetDevice(p->device));
-    PCS_TRY(upload_x(p, x));
-    PCS_TRY(pcs_normal_equations_dev(p, nullptr));
     cudaStream_t st = p->stream;
+    // host x -> device (pinned staging), then one launch: scatter + tables + cleared reduction targets
+    const double* x_dev = nullptr;
+    if (x && p->n_free > 0) {
+        PCS_TRY(ensure_pinned(p, p->n_free));
+        std::memcpy(p->h_pin, x, (size_t)p->n_free * 8);
+        PCS_CUDA(cudaMemcpyAsync(p->x, p->h_pin, (size_t)p->n_free * 8, cudaMemcpyHostToDevice, st));
+        x_dev = p->x;
+    }
+    PCS_TRY(launch_prepare(p, false, x_dev, p->ne, (p->V - p->ne) + (int64_t)p->M * 42));
+    // W is by far the largest output (720 B per segment): the evaluation runs in parts and the copy-out of a finished
+    // part's segments proceeds on a second stream while the next part is evaluated
+    const int n_parts = (W && p->n_seg >= 4096) ? 4 : 1;
+    if (n_parts > 1 && !p->copy_stream) {
+        PCS_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 8; ++k) PCS_CUDA(cudaEventCreateWithFlags(&p->part_done[k], cudaEventDisableTiming));
+        PCS_CUDA(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
+    }
+    for (int part = 0; part < n_parts; ++part) {
+        PCS_TRY(launch_normal_blocks(p, true, part, n_parts));
+        if (n_parts > 1) {
+            const int64_t s0 = p->h_part_bounds[part], s1 = p->h_part_bounds[part + 1];
+            PCS_CUDA(cudaEventRecord(p->part_done[part], st));
+            if (s1 > s0) {
+                PCS_CUDA(cudaStreamWaitEvent(p->copy_stream, p->part_done[part], 0));
+                PCS_CUDA(cudaMemcpyAsync(W + s0 * 90, p->W + s0 * 90, (size_t)(s1 - s0) * 90 * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+            }
+        }
+    }
     if (U) PCS_CUDA(cudaMemcpyAsync(U, p->U, (size_t)p->C * 225 * 8, cudaMemcpyDeviceToHost, st));
     if (gc) PCS_CUDA(cudaMemcpyAsync(gc, p->gc, (size_t)p->C * 15 * 8, cudaMemcpyDeviceToHost, st));
     if (V) PCS_CUDA(cudaMemcpyAsync(V, p->V, (size_t)p->M * 36 * 8, cudaMemcpyDeviceToHost, st));
     if (gp) PCS_CUDA(cudaMemcpyAsync(gp, p->gp, (size_t)p->M * 6 * 8, cudaMemcpyDeviceToHost, st));
-    if (W && p->n_seg) PCS_CUDA(cudaMemcpyAsync(W, p->W, (size_t)p->n_seg * 90 * 8, cudaMemcpyDeviceToHost, st));
+    if (W && p->n_seg && n_parts == 1) PCS_CUDA(cudaMemcpyAsync(W, p->W, (size_t)p->n_seg * 90 * 8, cudaMemcpyDeviceToHost, st));
     if (cost) PCS_CUDA(cudaMemcpyAsync(cost, p->cost, 8, cudaMemcpyDeviceToHost, st));
+    if (n_parts > 1) {
+        PCS_CUDA(cudaEventRecord(p->copy_done, p->copy_stream));
+        PCS_CUDA(cudaStreamWaitEvent(st, p->copy_done, 0));
+    }
     PCS_CUDA(cudaStreamSynchronize(st));
     return PCS_OK;
 }

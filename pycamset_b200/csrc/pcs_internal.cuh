@@ -88,8 +88,14 @@ struct pcs_problem {
     std::vector<cudaEvent_t> ev_a, ev_b;
     int64_t timing_count = 0;   // launches recorded since timing was enabled
 
-    int64_t* warp_seg = nullptr;  // [ne_warps + 1] segment range of every warp of the normal-equation kernel
-    int64_t ne_warps = 0;
+    // segment range tables of the normal-equation kernel, slot 0: single launch, slot 1: host path in parts
+    int64_t* warp_seg[2] = {nullptr, nullptr};  // [ne_parts][ne_warps + 1]
+    int64_t ne_warps[2] = {0, 0};
+    int ne_parts[2] = {0, 0};
+    std::vector<int64_t> h_part_bounds;   // [ne_parts + 1] first segment of every part (host copy)
+    cudaStream_t copy_stream = nullptr;    // host path: copy-out of finished parts overlaps the next part's kernel
+    cudaEvent_t part_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copy_done = nullptr;
     int64_t n_launches = 0;  // kernels launched by this library on behalf of the problem (pcs_launch_count)
 
     // peer-memory all-reduce state (pcs_p2p.cu)
@@ -106,7 +112,7 @@ int launch_prepare(pcs_problem* p, bool with_dR = false, const double* x_dev = n
                    int64_t n_zero = 0);
 int launch_residual(pcs_problem* p, double* r_dev);
 int launch_cost_only(pcs_problem* p, double* cost_dev);
-int launch_normal_blocks(pcs_problem* p, bool targets_cleared = false);
+int launch_normal_blocks(pcs_problem* p, bool targets_cleared = false, int part = 0, int n_parts = 1);
 int ensure_pinned(pcs_problem* p, int64_t doubles);
 void lm_free(pcs_problem* p);
 void p2p_free(pcs_problem* p);

@@ -360,36 +360,58 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     }
 }
 
-// Segment range of every warp: [lower_bound(seg_start, w N / n_warps), lower_bound(seg_start, (w + 1) N / n_warps)).
-// Depends only on the static problem structure; evaluated once per (problem, n_warps).
-__global__ void k_warp_ranges(int64_t N, int64_t n_seg, int n_warps, const int64_t* __restrict__ seg_start,
+// Segment range of every warp of every part.  The observation range is cut into `n_parts` equal parts and each part
+// into `n_warps` equal pieces; piece boundaries are moved to segment starts:
+//     warp_seg[part * (n_warps + 1) + w] = lower_bound(seg_start, N part / n_parts + (N / n_parts) w / n_warps).
+// Depends only on the static problem structure; evaluated once per (problem, n_warps, n_parts).
+__global__ void k_warp_ranges(int64_t N, int64_t n_seg, int n_warps, int n_parts, const int64_t* __restrict__ seg_start,
                               int64_t* __restrict__ warp_seg)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w > n_warps) return;
-    const int64_t target = N * w / n_warps;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_parts * (n_warps + 1)) return;
+    const int part = (int)(t / (n_warps + 1)), w = (int)(t % (n_warps + 1));
+    const int64_t lo_obs = N * part / n_parts, hi_obs = N * (part + 1) / n_parts;
+    const int64_t target = lo_obs + (hi_obs - lo_obs) * w / n_warps;
     int64_t lo = 0, hi = n_seg;
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (seg_start[mid] < target) lo = mid + 1; else hi = mid; }
-    warp_seg[w] = w == n_warps ? n_seg : lo;
+    warp_seg[t] = lo;
 }
 
-static int ensure_ranges(pcs_problem* p, int64_t n_ranges)
+static int ensure_ranges(pcs_problem* p, int64_t n_ranges, int n_parts)
 {
-    if (p->ne_warps == n_ranges) return PCS_OK;
-    if (p->warp_seg) cudaFree(p->warp_seg);
-    p->warp_seg = nullptr;
-    p->ne_warps = 0;
-    PCS_CUDA(cudaMalloc((void**)&p->warp_seg, (size_t)(n_ranges + 1) * sizeof(int64_t)));
-    k_warp_ranges<<<(int)((n_ranges + 128) / 128), 128, 0, p->stream>>>(p->N, p->n_seg, (int)n_ranges, p->seg_start, p->warp_seg);
+    const int slot = n_parts > 1 ? 1 : 0;
+    if (p->ne_warps[slot] == n_ranges && p->ne_parts[slot] == n_parts) return PCS_OK;
+    if (p->warp_seg[slot]) cudaFree(p->warp_seg[slot]);
+    p->warp_seg[slot] = nullptr;
+    p->ne_warps[slot] = 0;
+    const int64_t total = (int64_t)n_parts * (n_ranges + 1);
+    PCS_CUDA(cudaMalloc((void**)&p->warp_seg[slot], (size_t)total * sizeof(int64_t)));
+    k_warp_ranges<<<(int)((total + 127) / 128), 128, 0, p->stream>>>(p->N, p->n_seg, (int)n_ranges, n_parts, p->seg_start,
+                                                                     p->warp_seg[slot]);
     PCS_CUDA(cudaGetLastError());
-    p->ne_warps = n_ranges;
+    if (slot == 0) {
+        p->ne_warps[0] = n_ranges;
+        p->ne_parts[0] = 1;
+        return PCS_OK;
+    }
+    // segment boundaries of the parts, for the host-side pipelining of the W copy-out
+    p->h_part_bounds.assign(n_parts + 1, 0);
+    for (int k = 0; k < n_parts; ++k)
+        PCS_CUDA(cudaMemcpyAsync(&p->h_part_bounds[k], p->warp_seg[1] + (int64_t)k * (n_ranges + 1), sizeof(int64_t),
+                                 cudaMemcpyDeviceToHost, p->stream));
+    PCS_CUDA(cudaStreamSynchronize(p->stream));
+    p->h_part_bounds[n_parts] = p->n_seg;
+    p->ne_warps[1] = n_ranges;
+    p->ne_parts[1] = n_parts;
     return PCS_OK;
 }
 
-int launch_normal_blocks(pcs_problem* p, bool targets_cleared)
+// part / n_parts: evaluate only the observations of one part (host path: the copy-out of a part's W segments overlaps
+// the evaluation of the next part); n_parts = 1 evaluates everything in one launch.
+int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_parts)
 {
     // zero what is accumulated with reductions: [U | gc | cost | pad | V | gp]; W is fully overwritten
-    if (!targets_cleared) {
+    if (!targets_cleared && part == 0) {
         const int64_t zero_doubles = (p->V - p->ne) + (int64_t)p->M * 42;
         PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
     }
@@ -404,15 +426,16 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared)
         attr_set = true;
     }
     // persistent-style grid: `ctas` CTAs of NE_WARPS warps per SM; at least ~64 observations per warp
-    int64_t n_warps = std::min<int64_t>((p->N + 63) / 64, (int64_t)p->sm_count * ctas * NE_WARPS);
+    const int64_t n_part_obs = p->N / n_parts + 1;
+    int64_t n_warps = std::min<int64_t>((n_part_obs + 63) / 64, (int64_t)p->sm_count * ctas * NE_WARPS);
     n_warps = std::max<int64_t>(1, std::min<int64_t>(n_warps, p->n_seg));
-    PCS_TRY(ensure_ranges(p, n_warps));
+    PCS_TRY(ensure_ranges(p, n_warps, n_parts));
     const int grid = (int)((n_warps + NE_WARPS - 1) / NE_WARPS);
     const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
-    kern<<<grid, NE_WARPS * 32, smem, p->stream>>>((int)n_warps, p->warp_seg, p->s_cam, p->s_pose, p->s_key,
-                                                  (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab, p->tmpl,
-                                                  p->U, p->gc, p->cost, p->V, p->gp, p->W);
+    kern<<<grid, NE_WARPS * 32, smem, p->stream>>>((int)n_warps, p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1), p->s_cam, p->s_pose,
+                                                  p->s_key, (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
+                                                  p->tmpl, p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
     ++p->n_launches;
     if (p->timing) {
