@@ -457,7 +457,7 @@ int pcs_problem_destroy(pcs_problem* p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     lm_free(p);
     p2p_free(p);
-    dev_free(p->cam); dev_free(p->pose); dev_free(p->key); dev_free(p->uv); dev_free(p->tmpl);
+    dev_free(p->cam); dev_free(p->pose); dev_free(p->key); dev_free(p->uv); dev_free(p->tmpl); dev_free(p->tmpl4);
     dev_free(p->free_map); dev_free(p->free_idx); dev_free(p->cam_mask); dev_free(p->pose_mask); dev_free(p->key_mask);
     dev_free(p->row_prefix); dev_free(p->params); dev_free(p->x); dev_free(p->camtab); dev_free(p->posetab);
     dev_free(p->resid); dev_free(p->jvals); dev_free(p->seg_cam); dev_free(p->seg_pose); dev_free(p->seg_start);
@@ -499,6 +499,9 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     if (p->chain == PCS_CHAIN_TEMPLATE) {
         PCS_TRY(dev_alloc(&p->tmpl, 3 * (int64_t)p->K));
         PCS_CUDA(cudaMemcpyAsync(p->tmpl, d->template_xyz, (size_t)p->K * 24, cudaMemcpyHostToDevice, st));
+        PCS_TRY(dev_alloc(&p->tmpl4, 4 * (int64_t)p->K));
+        PCS_CUDA(cudaMemsetAsync(p->tmpl4, 0, (size_t)p->K * 32, st));
+        PCS_CUDA(cudaMemcpy2DAsync(p->tmpl4, 32, d->template_xyz, 24, 24, (size_t)p->K, cudaMemcpyHostToDevice, st));
     }
 
     // --- free map, masks, free index list (host, O(L)) ---------------------------------------

@@ -49,6 +49,7 @@ struct pcs_problem {
     double* uv = nullptr;
     // static tables
     double* tmpl = nullptr;        // [K][3] chain 0
+    double* tmpl4 = nullptr;       // [K][4] chain 0, padded rows for 16-byte loads (normal-equation kernel)
     int32_t* free_map = nullptr;   // [L]
     int32_t* free_idx = nullptr;   // [n_free] parameter-string position of free variable j
     uint16_t* cam_mask = nullptr;  // [C] bit k set = column k of [intr(9) extr(6)] is free

@@ -273,19 +273,34 @@ struct ObsJacCam {
     double Wc[6];
 };
 
+// Table rows are fetched with 16-byte loads (rows are 16-byte aligned): camera row doubles 0..21 = q(9) R(9) t(3)
+// (+1 unused), pose row doubles 0..11 = R(9) t(3); the template row is padded to 4 doubles.
 __device__ __forceinline__ void eval_obs_cam(const double* __restrict__ cam, const double* __restrict__ pose,
-                                             const double Xt[3], double u_obs, double v_obs, double res[2], ObsJacCam& J)
+                                             const double* __restrict__ pt4, double u_obs, double v_obs, double res[2],
+                                             ObsJacCam& J)
 {
-    double Xw[3], Yc[3], Xc[3];
-    transform(pose + POSE_R, pose + POSE_T, Xt, Xw);
-    rotate(cam + CAM_R, Xw, Yc);
+    double cv[22], pv[12], Xt[4];
+    {
+        const double2* c2 = reinterpret_cast<const double2*>(cam);
+        const double2* p2 = reinterpret_cast<const double2*>(pose);
+        const double2* x2 = reinterpret_cast<const double2*>(pt4);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) Xc[a] = Yc[a] + cam[CAM_T + a];
-    const Proj p = project(cam + CAM_Q, Xc);
+        for (int k = 0; k < 6; ++k) { const double2 v = p2[k]; pv[2 * k] = v.x; pv[2 * k + 1] = v.y; }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { const double2 v = x2[k]; Xt[2 * k] = v.x; Xt[2 * k + 1] = v.y; }
+#pragma unroll
+        for (int k = 0; k < 11; ++k) { const double2 v = c2[k]; cv[2 * k] = v.x; cv[2 * k + 1] = v.y; }
+    }
+    double Xw[3], Yc[3], Xc[3];
+    transform(pv + POSE_R, pv + POSE_T, Xt, Xw);
+    rotate(cv + CAM_R, Xw, Yc);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Xc[a] = Yc[a] + cv[CAM_T + a];
+    const Proj p = project(cv + CAM_Q, Xc);
     res[0] = p.u - u_obs;
     res[1] = p.v - v_obs;
     ObsJac full;
-    projection_jac(cam + CAM_Q, p, full);
+    projection_jac(cv + CAM_Q, p, full);
     J.xD = full.xD; J.yD = full.yD;
 #pragma unroll
     for (int k = 0; k < 5; ++k) { J.Au[k] = full.Au[k]; J.Av[k] = full.Av[k]; }

@@ -283,13 +283,11 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
             if (i < end) { c_n = s_cam[i]; m_n = s_pose[i]; k_n = s_key[i]; uv_n = s_uv[i]; }
         }
         if (lane < cnt) {
-            const double* pt = pts + 3 * (int64_t)k;
-            const double Xt[3] = {pt[0], pt[1], pt[2]};
             const double* ct = camtab + (int64_t)c * CAM_STRIDE;
             const double* ptab = posetab + (int64_t)m * POSE_STRIDE;
             double res[2];
             ObsJacCam J;
-            eval_obs_cam(ct, ptab, Xt, o.x, o.y, res, J);
+            eval_obs_cam(ct, ptab, pts + 4 * (int64_t)k, o.x, o.y, res, J);
             {
                 const double t0[8] = {J.xD, 1.0, 0.0, 0.0, J.Au[0], J.Au[1], J.Au[2], J.Au[3]};
                 const double t1[8] = {J.Au[4], J.Wc[0], J.Wc[1], J.Wc[2], J.Pm[0], J.Pm[1], J.Pm[2], res[0]};
@@ -435,7 +433,7 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
     kern<<<grid, NE_WARPS * 32, smem, p->stream>>>((int)n_warps, p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1), p->s_cam, p->s_pose,
                                                   p->s_key, (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
-                                                  p->tmpl, p->U, p->gc, p->cost, p->V, p->gp, p->W);
+                                                  p->tmpl4, p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
     ++p->n_launches;
     if (p->timing) {
