@@ -28,10 +28,10 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "Mobs/s residual+Jacobian+JtJ eval"
 ALGO_BYTES_PER_OBS = 28.0  # (u, v) 16 B + cam, pose, key 12 B; K_ne writes O(params), not O(N)
-# FP64 work of K_ne per observation: ~150 evaluation FMA-slots + 3 DMMA m8n8k4 (768 FMA slots issued,
-# ~420 of them structurally needed); 2 flop per FMA.
-FP64_ISSUED_FLOP_PER_OBS = 2.0 * (150 + 768)
-FP64_USEFUL_FLOP_PER_OBS = 2.0 * (150 + 420)
+# FP64 work of K_ne per observation: ~115 evaluation FMA slots + 1.5 DMMA m8n8k4 (384 FMA slots issued,
+# 272 of them are the upper triangle of the 16-column Gram update); 2 flop per FMA.
+FP64_ISSUED_FLOP_PER_OBS = 2.0 * (115 + 384 + 24)   # evaluation + 1.5 DMMA m8n8k4 + segment flush (6 DMMA / ~64 obs)
+FP64_USEFUL_FLOP_PER_OBS = 2.0 * (115 + 272)        # upper triangle of the 16 x 16 Gram update, 2 rows
 FP64_PEAK_TFLOPS = 36.9    # measured on this pool's B200 by tools/fp64_peak.cu (profiles/r1_fp64_peak_b200.json)
 
 WORKLOADS = {
@@ -177,9 +177,10 @@ def build_shard(args, rank, world, device):
                 detect_prob=detect_prob)
 
 
-def oracle_eval_mobs(sh, max_obs, min_seconds, threads=None):
-    """Time the CPU restatement (oracle port of the reference path) on a bounded sample of the workload:
-    residual + CSR Jacobian values + block J^T J / J^T r.  Returns (Mobs/s, n_obs_sample, cores, passes)."""
+def oracle_pass(sh, max_obs, threads=None):
+    """The CPU restatement (oracle port of the reference path) on a bounded sample of the workload.  Returns
+    (one_pass, n_obs_sample, cores): one_pass() evaluates residual + CSR Jacobian values + block J^T J / J^T r once.
+    The static structure (CSR pattern, segment ids) is built once outside, like the reference does."""
     from oracle import oracle as orc
     if threads:
         orc.set_threads(threads)
@@ -190,7 +191,7 @@ def oracle_eval_mobs(sh, max_obs, min_seconds, threads=None):
     C, M = sh["n_cams"], sh["n_poses"]
     o = orc.Problem(0, cam, pose, key, uv, C, M, 81, sh["rig"].template)
     fm = orc.free_map_from_mask(sh["unfixed"])
-    col, rp = o.csr_structure(fm)            # static structure: built once, like the reference (not timed)
+    col, rp = o.csr_structure(fm)
     pair = cam.astype(np.int64) * M + pose
     _, seg = np.unique(pair, return_inverse=True)
     seg = seg.astype(np.int32); n_seg = int(seg.max()) + 1 if n else 0
@@ -201,6 +202,12 @@ def oracle_eval_mobs(sh, max_obs, min_seconds, threads=None):
         o.csr_values(params, fm, rp)
         o.normal_blocks(params, seg, n_seg)
 
+    return one_pass, n, cores
+
+
+def oracle_eval_mobs(sh, max_obs, min_seconds, threads=None):
+    """Best-of-passes throughput of the oracle port over ~min_seconds: (Mobs/s, n_obs_sample, cores, passes)."""
+    one_pass, n, cores = oracle_pass(sh, max_obs, threads)
     one_pass()  # warm-up
     best, passes, t_all = float("inf"), 0, time.perf_counter()
     while passes < 3 or (time.perf_counter() - t_all) < min_seconds:
@@ -212,22 +219,26 @@ def oracle_eval_mobs(sh, max_obs, min_seconds, threads=None):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference path's CPU implementation (oracle port; the reference itself is Python +
-    numba and does not travel to the GPU box) on all host cores.  Rank 0 only."""
+    """--impl reference: the reference path's CPU implementation on all host cores.  The reference itself is
+    Python + numba and does not travel to the GPU box, so this is the oracle port (oracle/ba_oracle.c, OpenMP).
+    One step = one pass over a bounded sample of the workload; W warm-up passes, then exactly K timed passes.
+    Rank 0 only."""
     if rank != 0:
         return
-    sh = build_shard(args, 0, 1, "cpu")
     t0 = time.perf_counter()
-    vals = []
-    for step in range(args.warmup + args.steps):
-        mobs, n, cores, passes = oracle_eval_mobs(sh, args.cpu_sample_obs, 0.0)
-        if step >= args.warmup:
-            vals.append(mobs)
-    v = float(np.mean(vals))
-    sample = f"first {n} observations of {args.workload} (cam-major order), best of {passes} passes per step"
+    sh = build_shard(args, 0, 1, "cpu")
+    one_pass, n, cores = oracle_pass(sh, args.cpu_sample_obs)
+    for _ in range(max(args.warmup, 1)):
+        one_pass()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        one_pass()
+    dt = time.perf_counter() - t1
+    v = n * args.steps / dt / 1e6
+    sample = f"first {n} observations of {args.workload} (cam-major order), one pass per step"
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mobs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": n / v / 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": WORKLOADS[args.workload][4], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, sh, world),
         "cpu_baseline": {"value": v, "unit": "Mobs/s", "cores": cores, "kind": "port", "sample": sample},
