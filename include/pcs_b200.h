@@ -151,6 +151,16 @@ PCS_API int pcs_device_buffers_get(pcs_problem* p, pcs_device_buffers* out);
 typedef int (*pcs_allreduce_fn)(void* user, double* buf_dev, int64_t n, int op, void* stream);
 PCS_API int pcs_set_allreduce(pcs_problem* p, pcs_allreduce_fn fn, void* user, int rank, int world_size);
 
+/* Initialiser cost evaluation: bundle_adjustment_costfn (compiled_helpers.py:517-549, distortion :438-460) as
+ * estimate_camera_relative_poses drives it (template_handler.py:510-593) -- all `n_tables` candidate pose tables in
+ * one call over the problem's resident observations.
+ *   im_points  [n_tables][M][K][3]  target points transformed by each image's candidate pose
+ *   proj [C][3][4] = K_c [R_c | t_c],  intrinsics [C][3][3],  dists [C][5] = (k1, k2, p1, p2, k3)
+ *   errors     [n_tables][2N] projected-minus-measured pixels, dd row order (or NULL to skip: 16 B/obs/table of PCIe)
+ *   per_image  [n_tables][M]  sum over the observations of image m of |error| (template_handler.py:550-560), or NULL */
+PCS_API int pcs_costfn(pcs_problem* p, int n_tables, const double* im_points, const double* proj, const double* intrinsics,
+                       const double* dists, double* errors, double* per_image);
+
 /* Multi-GPU, raw evaluation: one-shot all-reduce (sum, rank order) of the camera blocks [U | gc | cost] over NVLink
  * peer memory -- the only exchange step of a pose-sharded normal-equation evaluation (C * 240 + 1 doubles, latency
  * bound).  Every rank allocates a zero-initialised buffer of pcs_p2p_buffer_bytes(p, world) that all peers have mapped

@@ -495,3 +495,40 @@ ORACLE_API void oracle_block_rigid(const double *p, const double *X, double *fun
 }
 
 ORACLE_API void oracle_block_rodrigues_jac(const double *r, double *out27) { rodrigues_jac(r, out27); }
+
+/* ------------------------------------------------------------------------------------------------
+ * Initialiser cost evaluation.
+ * compiled_helpers.py:517-549 numpy_bundle_adjustment_costfn with :438-460 nb_distort_prealloc, called once per
+ * candidate pose table by estimate_camera_relative_poses (template_handler.py:510-593):
+ *   p = P_c [X; 1],  (u, v) = (p0 / p2, p1 / p2),  Brown-Conrady distortion applied in PIXEL space around the
+ *   principal point (x = (u - cx) / fx, ...),  error = distorted - measured.
+ * im_points: [M][K][3] target points already transformed by the candidate pose of every image;
+ * proj: [C][3][4] = K_c [R_c | t_c];  ints: [C][3][3];  dists: [C][5] = (k1, k2, p1, p2, k3).
+ * errors_out: [2N] interleaved (x, y) in dd row order.
+ * ---------------------------------------------------------------------------------------------- */
+ORACLE_API int oracle_costfn(int64_t N, const int32_t *cam, const int32_t *pose, const int32_t *key,
+                             const double *uv, int C, int M, int K, const double *im_points, const double *proj,
+                             const double *ints, const double *dists, double *errors_out)
+{
+    (void)C; (void)M;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        const double *P = proj + 12 * (int64_t)cam[i];
+        const double *A = ints + 9 * (int64_t)cam[i];
+        const double *k = dists + 5 * (int64_t)cam[i];
+        const double *X = im_points + 3 * ((int64_t)pose[i] * K + key[i]);
+        double p[3];
+        for (int r = 0; r < 3; ++r) p[r] = P[4 * r] * X[0] + P[4 * r + 1] * X[1] + P[4 * r + 2] * X[2] + P[4 * r + 3];
+        const double u = p[0] / p[2], v = p[1] / p[2];
+        const double c0 = A[2], c1 = A[5], f0 = A[0], f1 = A[4];
+        const double x = (u - c0) / f0, y = (v - c1) / f1;
+        const double r2 = x * x + y * y;
+        const double kup = 1 + k[0] * r2 + k[1] * (r2 * r2) + k[4] * (r2 * r2 * r2);
+        double xD = x * kup, yD = y * kup;
+        xD += 2 * k[2] * x * y + k[3] * (r2 + 2 * (x * x));
+        yD += k[2] * (r2 + 2 * (y * y)) + 2 * k[3] * x * y;
+        errors_out[2 * i] = xD * f0 + c0 - uv[2 * i];
+        errors_out[2 * i + 1] = yD * f1 + c1 - uv[2 * i + 1];
+    }
+    return 0;
+}

@@ -148,6 +148,23 @@ class Problem:
         return U, gc, V, gp, W, cost.value
 
 
+def costfn(dd, im_points, proj, ints, dists):
+    """Restatement of numpy_bundle_adjustment_costfn (compiled_helpers.py:517-549): errors (2N,) in dd row order."""
+    dd = np.asarray(dd, np.float64)
+    cam = np.ascontiguousarray(dd[:, 0], np.int32); pose = np.ascontiguousarray(dd[:, 1], np.int32)
+    key = np.ascontiguousarray(dd[:, 2], np.int32); uv = np.ascontiguousarray(dd[:, 3:5], np.float64)
+    im_points = np.ascontiguousarray(im_points, np.float64)
+    M, K = im_points.shape[0], im_points.shape[1]
+    proj = np.ascontiguousarray(proj, np.float64); ints = np.ascontiguousarray(ints, np.float64)
+    dists = np.ascontiguousarray(np.asarray(dists, np.float64).reshape(-1, 5))
+    out = np.empty(2 * dd.shape[0])
+    f = lib().oracle_costfn
+    f.argtypes = [ct.c_int64, _i32p, _i32p, _i32p, _f64p, ct.c_int, ct.c_int, ct.c_int, _f64p, _f64p, _f64p, _f64p, _f64p]
+    f(ct.c_int64(dd.shape[0]), cam, pose, key, uv, proj.shape[0], M, K, im_points.reshape(-1), proj.reshape(-1),
+      ints.reshape(-1), dists.reshape(-1), out)
+    return out
+
+
 def set_threads(n: int) -> None:
     lib().oracle_set_threads(int(n))
 

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "pcs_csr_structure", "pcs_jacobian_values", "pcs_jacobian_values_dev", "pcs_segments", "pcs_normal_equations",
     "pcs_normal_equations_dev", "pcs_normal_dense", "pcs_device_buffers_get", "pcs_set_allreduce",
     "pcs_lm_default_options", "pcs_lm_solve", "pcs_timing_enable", "pcs_timing_get", "pcs_timing_get_all", "pcs_launch_count",
-    "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_device_sm_count",
+    "pcs_costfn", "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_device_sm_count",
     "pcs_version",
 ]
 
@@ -114,6 +114,7 @@ def load() -> ct.CDLL:
     lib.pcs_timing_get.argtypes = [vp, ct.POINTER(ct.c_double)]
     lib.pcs_timing_get_all.argtypes = [vp, vp, ct.c_int64, ct.POINTER(ct.c_int64)]
     lib.pcs_launch_count.argtypes = [vp, ct.POINTER(ct.c_int64)]
+    lib.pcs_costfn.argtypes = [vp, ct.c_int, vp, vp, vp, vp, vp, vp]
     lib.pcs_p2p_buffer_bytes.argtypes = [vp, ct.c_int]
     lib.pcs_p2p_buffer_bytes.restype = ct.c_int64
     lib.pcs_p2p_allreduce_setup.argtypes = [vp, ct.c_int, ct.c_int, ct.POINTER(vp), ct.c_int64]

@@ -214,3 +214,30 @@ def run_bundle_adjustment(param_handler, threads: int = 1, device: int = 0, solv
     if camset is not None and hasattr(camset, "set_calibration_history"):
         camset.set_calibration_history(result, handler)
     return result, camset
+
+
+class GpuCostFn:
+    """Drop-in for compiled_helpers.bundle_adjustment_costfn as estimate_camera_relative_poses uses it
+    (template_handler.py:510-593): the observation table is uploaded once, every call scores one or many candidate
+    pose tables.
+
+        cost = GpuCostFn(dd, n_cams, n_poses, n_keys)
+        errors = cost(imlocs, proj, ints, dists)                        # (2N,) like the reference
+        errors, per_image = cost.batch(tables, proj, ints, dists)       # all candidates at once, per-image sums on the GPU
+    """
+
+    def __init__(self, dd, n_cams, n_poses, n_keys, device: int = 0):
+        dd = np.asarray(dd, np.float64)
+        self.problem = BundleProblem(L.CHAIN_TEMPLATE, dd[:, 0], dd[:, 1], dd[:, 2], dd[:, 3:5], n_cams, n_poses, n_keys,
+                                     template=np.zeros((n_keys, 3)), device=device)
+
+    def __call__(self, im_points, projection_matrixes, intrinsics, dists):
+        e, _ = self.problem.costfn(np.asarray(im_points).reshape(self.problem.n_poses, self.problem.n_keys, 3),
+                                   projection_matrixes, intrinsics, dists, errors=True, per_image=False)
+        return e[0]
+
+    def batch(self, tables, projection_matrixes, intrinsics, dists, errors=True):
+        return self.problem.costfn(tables, projection_matrixes, intrinsics, dists, errors=errors, per_image=True)
+
+    def close(self):
+        self.problem.close()

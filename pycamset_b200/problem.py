@@ -232,6 +232,24 @@ class BundleProblem:
         L.check(self._lib.pcs_launch_count(self._h, ct.byref(n)))
         return n.value
 
+    def costfn(self, im_points, proj, ints, dists, errors=True, per_image=True):
+        """Initialiser cost evaluation over all candidate tables at once (pcs_costfn).
+        im_points: (B, M, K, 3) or (M, K, 3).  Returns (errors (B, 2N) or None, per_image (B, M) or None)."""
+        im_points = np.ascontiguousarray(im_points, np.float64)
+        if im_points.ndim == 3:
+            im_points = im_points[None]
+        B = im_points.shape[0]
+        if im_points.shape[1:] != (self.n_poses, self.n_keys, 3):
+            raise ValueError(f"im_points must be (B, {self.n_poses}, {self.n_keys}, 3), got {im_points.shape}")
+        proj = np.ascontiguousarray(proj, np.float64); ints = np.ascontiguousarray(ints, np.float64)
+        dists = np.ascontiguousarray(np.asarray(dists, np.float64).reshape(-1, 5))
+        if proj.shape != (self.n_cams, 3, 4) or ints.shape != (self.n_cams, 3, 3) or dists.shape[0] != self.n_cams:
+            raise ValueError("proj / ints / dists must be (C, 3, 4) / (C, 3, 3) / (C, 5)")
+        e = np.empty((B, 2 * self.n_obs)) if errors else None
+        pi = np.empty((B, self.n_poses)) if per_image else None
+        L.check(self._lib.pcs_costfn(self._h, B, _ptr(im_points), _ptr(proj), _ptr(ints), _ptr(dists), _ptr(e), _ptr(pi)))
+        return e, pi
+
     def p2p_buffer_bytes(self, world_size) -> int:
         return int(self._lib.pcs_p2p_buffer_bytes(self._h, int(world_size)))
 

@@ -133,6 +133,38 @@ def block_goldens():
     print("[golden] blocks: 16 random points per block")
 
 
+def costfn_golden():
+    """Initialiser cost evaluation: estimate_camera_relative_poses evaluates
+    ch.bundle_adjustment_costfn once per candidate pose table (template_handler.py:510-593,
+    compiled_helpers.py:517-549).  Dumps its inputs and outputs for a seeded ring with B candidate tables, plus the
+    per-image sums of the per-observation error norms the initialiser reduces them to (:550-560)."""
+    from pyCamSet.optimisation import compiled_helpers as ch
+    from pyCamSet.utils.general_utils import h_tform, make_4x4h_tform
+    from pycamset_b200 import synthetic as syn
+
+    C, M, B = 5, 7, 4
+    rig = syn.make_rig(C, M, layout="ring", distortion=True, seed=17, detect_prob=0.8)
+    rng = np.random.default_rng(99)
+    dd = rig.dd()
+    ints = np.zeros((C, 3, 3)); dists = np.zeros((C, 5)); proj = np.zeros((C, 3, 4))
+    for c in range(C):
+        fx, px, fy, py, k1, k2, p1, p2, k3 = rig.intr[c]
+        ints[c] = [[fx, 0, px], [0, fy, py], [0, 0, 1]]
+        dists[c] = [k1, k2, p1, p2, k3]
+        proj[c] = ints[c] @ make_4x4h_tform(rig.extr[c, :3], rig.extr[c, 3:])[:3, :]
+    tables = np.empty((B, M, rig.template.shape[0], 3))
+    for b in range(B):   # candidate pose tables: the truth and perturbed copies (one per reference camera in the initialiser)
+        for m in range(M):
+            pose = rig.poses[m] + (0 if b == 0 else 1e-2 * rng.normal(size=6))
+            tables[b, m] = h_tform(rig.template, make_4x4h_tform(pose[:3], pose[3:]))
+    errors = np.stack([ch.bundle_adjustment_costfn(dd, tables[b], proj, ints, dists) for b in range(B)])
+    norms = np.sqrt(np.sum(errors.reshape(B, -1, 2) ** 2, axis=2))
+    per_image = np.stack([[np.sum(norms[b][dd[:, 1] == m]) for m in range(M)] for b in range(B)])
+    np.savez_compressed(HERE / "costfn.npz", dd=dd, tables=tables, proj=proj, ints=ints, dists=dists, errors=errors,
+                        per_image=per_image, n_cams=np.int32(C), n_poses=np.int32(M))
+    print(f"[golden] costfn: N={dd.shape[0]} B={B} mean |e| = {norms.mean():.3f} px")
+
+
 def ccube_goldens():
     """Configs 2 and 3: the reference's own test paths (tests/calibrate_ccube_test.py:6-19,
     tests/self_calibrate_ccube_test.py:10-37), dumped at the initial and at the final iterate."""
@@ -163,9 +195,13 @@ def ccube_goldens():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-ccube", action="store_true")
+    ap.add_argument("--only-costfn", action="store_true")
     args = ap.parse_args()
     import pyCamSet
     assert "baseline/_ref" in pyCamSet.__file__, pyCamSet.__file__
+    costfn_golden()
+    if args.only_costfn:
+        return 0
     block_goldens()
     rig, th, x_t, sh, x_s = synthetic_handlers(seed=3, n_cams=4, n_poses=6, detect_prob=0.8)
     dump_case("ring4_template", th, x_t)

@@ -103,3 +103,14 @@ def test_block_normal_equations_match_dense(case):
         ref = JtJ[np.ix_(ci, mi)]
         assert np.max(np.abs(W[s] - ref)) <= tol * max(1.0, np.abs(ref).max())
     assert abs(cost - cost2) <= 1e-12 * cost
+
+
+def test_costfn_oracle_against_reference():
+    """Initialiser cost evaluation: oracle restatement vs the reference's bundle_adjustment_costfn outputs."""
+    g = dict(np.load(GOLDEN / "costfn.npz"))
+    for b in range(g["tables"].shape[0]):
+        e = orc.costfn(g["dd"], g["tables"][b], g["proj"], g["ints"], g["dists"])
+        assert np.max(np.abs(e - g["errors"][b])) < 1e-9
+        norms = np.sqrt(np.sum(e.reshape(-1, 2) ** 2, axis=1))
+        pi = np.bincount(g["dd"][:, 1].astype(int), weights=norms, minlength=int(g["n_poses"]))
+        assert np.max(np.abs(pi - g["per_image"][b]) / g["per_image"][b]) < 1e-12
