@@ -20,9 +20,9 @@
 //   * The Gram update  G += J'^T J'  runs on the FP64 tensor path: per 2 observations (4 rows = one k-step) the warp
 //     loads 2 fragment values per lane and issues 3 DMMA m8n8k4 (tile pairs AA, AB, BB).  A-fragment and B-fragment
 //     of a tile are the same register.
-//   * Two accumulator sets: the segment's (flushed per segment through a 2 KB shared scratch: W by coalesced plain
-//     stores -- the warp owns the segment -- V/g_m by FP64 reductions) and the camera's (U_c, g_c, r.r; flushed when
-//     the camera changes).
+//   * Two accumulator sets: the segment's (registers; flushed per segment on the tensor path: W by 16-byte plain
+//     stores -- the warp owns the segment -- V/g_m by FP64 reductions) and the camera's running sums (U_c, g_c, r.r;
+//     a 16 x 16 block in shared memory, flushed when the camera changes).
 //   * Rotation rows are accumulated in the tangent parametrisation; the SO(3) left Jacobians are applied once per
 //     block inside the flushes (Jl_m folded into the adjoint, Jl_c on three rows of W_s and on U_c / g_c).
 //   HBM traffic per observation: (u,v) 16 B + camera, pose, key 12 B = 28 B read; outputs are O(segments).
@@ -35,8 +35,9 @@
 namespace pcs {
 
 constexpr int NE_WARPS = 4;                  // warps per CTA
+constexpr int NE_GLD = 17;                   // row stride of the camera-sum scratch (odd: conflict-free column access)
 constexpr int NE_TILE_DOUBLES = 64 * 8;      // one 8-column tile of the 64 staged rows
-constexpr int NE_SCRATCH_DOUBLES = 64 + 256;           // Tbar (8 x 8, flush_segment) | camera block (16 x 16, flush_camera)
+constexpr int NE_SCRATCH_DOUBLES = 64 + 16 * NE_GLD;   // Tbar (8 x 8, flush_segment) | running camera sums (16 x 16)
 constexpr int NE_WARP_DOUBLES = 2 * NE_TILE_DOUBLES + NE_SCRATCH_DOUBLES;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
@@ -97,17 +98,17 @@ __device__ __forceinline__ void tile_times_tbar(const double x[2], double tb0, d
 
 // Segment flush.  S = this segment's camera Gram matrix G_s (fragments: aa = G[0:8,0:8], ab = G[0:8,8:16],
 // bb = G[8:16,8:16]; column 8 + kk with kk = 0: k3, 1..3: camera rotation (tangent), 4..6: camera translation, 7: r).
-// C = the running camera sums.  With the adjoint folded with the pose's left Jacobian,
+// G = the running camera sums (shared memory).  With the adjoint folded with the pose's left Jacobian,
 //     T' = [[R_c Jl_m, 0], [[s]x R_c Jl_m, R_c]],  s = R_c t_m,
 // embedded as Tbar[1..6][0..5] = T', Tbar[7][6] = 1 (zero elsewhere), the pose blocks are three small products
 // on the FP64 tensor path:
 //     Wbar_A = ab Tbar, Wbar_B = bb Tbar   -> W_s[a][j] (a < 15, j < 6), final in the pose columns
 //     Vbar   = Tbar^T Wbar_B               -> V_m += Vbar[0:6,0:6], g_m += Vbar[0:6,6]
 // Rows 9..11 of W_s are then rotated from the camera's tangent frame with Jl_c (three shuffled rows).
-__device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int64_t seg, int c, int m,
+__device__ __forceinline__ void flush_segment(NeAcc& S, int lane, int64_t seg, int c, int m,
                                               const double* __restrict__ camtab, const double* __restrict__ posetab,
-                                              double* __restrict__ tbar, double* __restrict__ V, double* __restrict__ gp,
-                                              double* __restrict__ W)
+                                              double* __restrict__ tbar, double* __restrict__ G, double* __restrict__ V,
+                                              double* __restrict__ gp, double* __restrict__ W)
 {
     if (lane < 9) {
         const double* Rc = camtab + (int64_t)c * CAM_STRIDE + CAM_R;
@@ -125,8 +126,17 @@ __device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int6
         tbar[(4 + i) * 8 + j] = s1 * q2 - s2 * q1;                                          // ([s]x R_c Jl_m)[i][j]
         tbar[(4 + i) * 8 + 3 + j] = Rc[3 * i + j];
     }
+    {   // fold the segment into the running camera sums (full symmetric 16 x 16 in shared memory)
+        const int row = lane >> 2, cp = 2 * (lane & 3);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) { C.aa[i] += S.aa[i]; C.ab[i] += S.ab[i]; C.bb[i] += S.bb[i]; }
+        for (int i = 0; i < 2; ++i) {
+            const int col = cp + i;
+            G[row * NE_GLD + col] += S.aa[i];
+            G[row * NE_GLD + 8 + col] += S.ab[i];
+            G[(8 + col) * NE_GLD + row] += S.ab[i];
+            G[(8 + row) * NE_GLD + 8 + col] += S.bb[i];
+        }
+    }
     __syncwarp();
     const double tb0 = tbar[(lane & 3) * 8 + (lane >> 2)], tb1 = tbar[(4 + (lane & 3)) * 8 + (lane >> 2)];
     double wa[2], wb[2];
@@ -170,45 +180,37 @@ __device__ __forceinline__ void flush_segment(NeAcc& S, NeAcc& C, int lane, int6
     acc_zero(S);
 }
 
-// Camera flush: the running camera sums (tangent parametrisation) go through a 16 x 16 shared scratch, are mapped
+// Camera flush: the running camera sums (tangent parametrisation, 16 x 16 in shared memory) are mapped
 // to the reference's rvec parametrisation, B = T^T B' T with T = diag(I9, Jl_c, I3, 1), and are added to U_c
 // (both triangles), g_c and r.r with FP64 reductions.  Runs once per (warp, camera): cost is irrelevant.
-__device__ __forceinline__ void flush_camera(NeAcc& C, int lane, int c, const double* __restrict__ camtab,
+__device__ __forceinline__ void flush_camera(int lane, int c, const double* __restrict__ camtab,
                                              double* __restrict__ G, double* __restrict__ U, double* __restrict__ gc,
                                              double* __restrict__ cost)
 {
-    const int row = lane >> 2, cp = 2 * (lane & 3);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int col = cp + i;
-        G[row * 16 + col] = C.aa[i];
-        G[row * 16 + 8 + col] = C.ab[i];
-        G[(8 + col) * 16 + row] = C.ab[i];
-        G[(8 + row) * 16 + 8 + col] = C.bb[i];
-    }
-    acc_zero(C);
     const double* jl = camtab + (int64_t)c * CAM_STRIDE + CAM_JL;
     const double j[9] = {jl[0], jl[1], jl[2], jl[3], jl[4], jl[5], jl[6], jl[7], jl[8]};
     __syncwarp();
     if (lane < 16) {  // columns 9..11 of row `lane`  <-  row * Jl
-        const double a0 = G[lane * 16 + 9], a1 = G[lane * 16 + 10], a2 = G[lane * 16 + 11];
+        const double a0 = G[lane * NE_GLD + 9], a1 = G[lane * NE_GLD + 10], a2 = G[lane * NE_GLD + 11];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) G[lane * 16 + 9 + i] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
+        for (int i = 0; i < 3; ++i) G[lane * NE_GLD + 9 + i] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
     }
     __syncwarp();
     if (lane < 16) {  // rows 9..11 of column `lane`  <-  Jl^T * column
-        const double a0 = G[9 * 16 + lane], a1 = G[10 * 16 + lane], a2 = G[11 * 16 + lane];
+        const double a0 = G[9 * NE_GLD + lane], a1 = G[10 * NE_GLD + lane], a2 = G[11 * NE_GLD + lane];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) G[(9 + i) * 16 + lane] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
+        for (int i = 0; i < 3; ++i) G[(9 + i) * NE_GLD + lane] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
     }
     __syncwarp();
     double* Uc = U + (int64_t)c * 225;
     for (int e = lane; e < 225; e += 32) {
         const int a = e / 15, b = e - 15 * a;
-        atomicAdd(Uc + e, G[a * 16 + b]);
+        atomicAdd(Uc + e, G[a * NE_GLD + b]);
     }
-    if (lane < 15) atomicAdd(gc + (int64_t)c * 15 + lane, G[lane * 16 + 15]);
-    if (lane == 15) atomicAdd(cost, G[15 * 16 + 15]);
+    if (lane < 15) atomicAdd(gc + (int64_t)c * 15 + lane, G[lane * NE_GLD + 15]);
+    if (lane == 15) atomicAdd(cost, G[15 * NE_GLD + 15]);
+    __syncwarp();
+    for (int e = lane; e < 16 * NE_GLD; e += 32) G[e] = 0.0;   // the sums restart with the next camera
     __syncwarp();
 }
 
@@ -230,8 +232,8 @@ __device__ __forceinline__ void gram_step(NeAcc& S, const double* __restrict__ w
     dmma884(S.bb[0], S.bb[1], v1, v1);
 }
 
-template <int CTAS_PER_SM>
-__global__ void __launch_bounds__(NE_WARPS * 32, CTAS_PER_SM)
+template <int CTAS_PER_SM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
 k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_pose,
          const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv, const int64_t* __restrict__ seg_start,
          const double* __restrict__ camtab, const double* __restrict__ posetab, const double* __restrict__ pts,
@@ -241,7 +243,7 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     extern __shared__ __align__(16) double ne_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* ws = ne_smem + warp * NE_WARP_DOUBLES;
-    const int wg = blockIdx.x * NE_WARPS + warp;
+    const int wg = blockIdx.x * WARPS + warp;
     if (wg >= n_warps) return;
 
     // this warp's range of whole segments (k_warp_ranges)
@@ -249,12 +251,12 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     if (sb >= se) return;
     const int64_t begin = seg_start[sb], end = seg_start[se];
 
-    NeAcc S, C;   // segment / camera accumulators
+    NeAcc S;   // the segment's accumulators; the camera's running sums live in shared memory
     acc_zero(S);
-    acc_zero(C);
     double* const scratch = ws + 2 * NE_TILE_DOUBLES;   // Tbar: constant entries are written once
     scratch[lane] = 0.0;
     scratch[32 + lane] = lane == 30 ? 1.0 : 0.0;       // Tbar[7][6] = 1
+    for (int e = lane; e < 16 * NE_GLD; e += 32) scratch[64 + e] = 0.0;
     __syncwarp();
     int64_t cur_seg = sb - 1;   // segments are visited in order: a piece head advances this counter
     int cur_c = -1, cur_m = -1;
@@ -318,9 +320,9 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
             pieces &= pieces - 1;
             const int b = pieces ? __ffs(pieces) - 1 : cnt;
             if ((heads >> a) & 1u) {
-                if (cur_c >= 0) flush_segment(S, C, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, V, gp, W);
+                if (cur_c >= 0) flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
                 const int nc = __shfl_sync(0xffffffffu, c, a);
-                if (nc != cur_c && cur_c >= 0) flush_camera(C, lane, cur_c, camtab, scratch + 64, U, gc, cost);
+                if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
                 ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
             }
             // k-steps of the piece: boundary steps shared with a neighbouring piece (odd a / odd b) are masked,
@@ -353,8 +355,8 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
         __syncwarp();
     }
     if (cur_c >= 0) {
-        flush_segment(S, C, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, V, gp, W);
-        flush_camera(C, lane, cur_c, camtab, scratch + 64, U, gc, cost);
+        flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
+        flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
     }
 }
 
@@ -414,24 +416,27 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
         PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
     }
     if (p->N == 0) return PCS_OK;
-    // resident CTAs per SM: 4 x 128 registers (default) or 3 x 154; PCS_NE_CTAS=3 selects the latter for A/B runs
-    static const int ctas = [] { const char* e = std::getenv("PCS_NE_CTAS"); return e && e[0] >= '3' && e[0] <= '5' ? e[0] - '0' : 4; }();
-    auto kern = ctas == 3 ? k_normal<3> : ctas == 5 ? k_normal<5> : k_normal<4>;
+    // occupancy variants (PCS_NE_CFG for A/B runs): 3 = 5 CTAs x 4 warps, 96 registers, no spills (default, 20 warps/SM:
+    // the shared-memory limit at 10.9 KB per warp), 0 = 4 CTAs x 4 warps (124 registers), 1 = 3 CTAs x 6 warps (96),
+    // 2 = 3 CTAs x 4 warps (142).  Measured on config 4: 0.132 / 0.138 / 0.144 / 0.149 ms.
+    static const int cfg = [] { const char* e = std::getenv("PCS_NE_CFG"); return e && e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 3; }();
+    const int ctas = cfg == 0 ? 4 : cfg == 3 ? 5 : 3, warps = cfg == 1 ? 6 : 4;
+    auto kern = cfg == 0 ? k_normal<4, 4> : cfg == 1 ? k_normal<3, 6> : cfg == 2 ? k_normal<3, 4> : k_normal<5, 4>;
     static bool attr_set = false;
-    const size_t smem = (size_t)NE_WARPS * NE_WARP_DOUBLES * sizeof(double);
+    const size_t smem = (size_t)warps * NE_WARP_DOUBLES * sizeof(double);
     if (!attr_set) {
         PCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    // persistent-style grid: `ctas` CTAs of NE_WARPS warps per SM; at least ~64 observations per warp
+    // persistent-style grid: `ctas` CTAs of `warps` warps per SM; at least ~64 observations per warp
     const int64_t n_part_obs = p->N / n_parts + 1;
-    int64_t n_warps = std::min<int64_t>((n_part_obs + 63) / 64, (int64_t)p->sm_count * ctas * NE_WARPS);
+    int64_t n_warps = std::min<int64_t>((n_part_obs + 63) / 64, (int64_t)p->sm_count * ctas * warps);
     n_warps = std::max<int64_t>(1, std::min<int64_t>(n_warps, p->n_seg));
     PCS_TRY(ensure_ranges(p, n_warps, n_parts));
-    const int grid = (int)((n_warps + NE_WARPS - 1) / NE_WARPS);
+    const int grid = (int)((n_warps + warps - 1) / warps);
     const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
-    kern<<<grid, NE_WARPS * 32, smem, p->stream>>>((int)n_warps, p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1), p->s_cam, p->s_pose,
+    kern<<<grid, warps * 32, smem, p->stream>>>((int)n_warps, p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1), p->s_cam, p->s_pose,
                                                   p->s_key, (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
                                                   p->tmpl4, p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
