@@ -35,9 +35,8 @@
 namespace pcs {
 
 constexpr int NE_WARPS = 4;                  // warps per CTA
-constexpr int NE_GLD = 17;                   // row stride of the camera-sum scratch (odd: conflict-free column access)
 constexpr int NE_TILE_DOUBLES = 64 * 8;      // one 8-column tile of the 64 staged rows
-constexpr int NE_SCRATCH_DOUBLES = 64 + 16 * NE_GLD;   // Tbar (8 x 8, flush_segment) | running camera sums (16 x 16)
+constexpr int NE_SCRATCH_DOUBLES = 64 + 192;           // Tbar (8 x 8, flush_segment) | running camera sums (tiles AA, AB, BB)
 constexpr int NE_WARP_DOUBLES = 2 * NE_TILE_DOUBLES + NE_SCRATCH_DOUBLES;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
@@ -74,6 +73,18 @@ struct NeAcc {
 };
 
 __device__ __forceinline__ void acc_zero(NeAcc& A) { A.aa[0] = A.aa[1] = A.ab[0] = A.ab[1] = A.bb[0] = A.bb[1] = 0.0; }
+
+// Running camera sums: tiles AA = G[0:8,0:8], AB = G[0:8,8:16], BB = G[8:16,8:16] of the symmetric 16 x 16 matrix,
+// 64 doubles each; element (row, col) of a tile sits at row * 8 + (col ^ bit1(row)), which makes the per-lane
+// read-modify-write of flush_segment (rows lane >> 2, columns 2 (lane & 3) + i) bank-conflict free.
+__device__ __forceinline__ int cam_tile_pos(int row, int col) { return row * 8 + (col ^ ((row >> 1) & 1)); }
+__device__ __forceinline__ double cam_sum(const double* __restrict__ G, int a, int b)   // G(a, b), 0 <= a, b < 16
+{
+    if (a > b) { const int t = a; a = b; b = t; }
+    if (b < 8) return G[cam_tile_pos(a, b)];
+    if (a < 8) return G[64 + cam_tile_pos(a, b - 8)];
+    return G[128 + cam_tile_pos(a - 8, b - 8)];
+}
 
 // double-precision shuffle of one of two registers: returns (sel ? x1 : x0) of lane `src`
 __device__ __forceinline__ double shfl_pick(double x0, double x1, int src, bool sel)
@@ -126,15 +137,14 @@ __device__ __forceinline__ void flush_segment(NeAcc& S, int lane, int64_t seg, i
         tbar[(4 + i) * 8 + j] = s1 * q2 - s2 * q1;                                          // ([s]x R_c Jl_m)[i][j]
         tbar[(4 + i) * 8 + 3 + j] = Rc[3 * i + j];
     }
-    {   // fold the segment into the running camera sums (full symmetric 16 x 16 in shared memory)
+    {   // fold the segment into the running camera sums (three 8 x 8 tiles in shared memory, bank-conflict free)
         const int row = lane >> 2, cp = 2 * (lane & 3);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int col = cp + i;
-            G[row * NE_GLD + col] += S.aa[i];
-            G[row * NE_GLD + 8 + col] += S.ab[i];
-            G[(8 + col) * NE_GLD + row] += S.ab[i];
-            G[(8 + row) * NE_GLD + 8 + col] += S.bb[i];
+            const int e = cam_tile_pos(row, cp + i);
+            G[e] += S.aa[i];
+            G[64 + e] += S.ab[i];
+            G[128 + e] += S.bb[i];
         }
     }
     __syncwarp();
@@ -180,37 +190,40 @@ __device__ __forceinline__ void flush_segment(NeAcc& S, int lane, int64_t seg, i
     acc_zero(S);
 }
 
-// Camera flush: the running camera sums (tangent parametrisation, 16 x 16 in shared memory) are mapped
-// to the reference's rvec parametrisation, B = T^T B' T with T = diag(I9, Jl_c, I3, 1), and are added to U_c
-// (both triangles), g_c and r.r with FP64 reductions.  Runs once per (warp, camera): cost is irrelevant.
+// Camera flush: the running camera sums (tangent parametrisation, shared memory) are mapped to the reference's
+// rvec parametrisation, B = T^T B' T with T = diag(I9, Jl_c, I3, 1), and added to U_c (both triangles), g_c and r.r
+// with FP64 reductions: every output entry is formed from at most 9 tile entries.  Runs once per (warp, camera).
 __device__ __forceinline__ void flush_camera(int lane, int c, const double* __restrict__ camtab,
                                              double* __restrict__ G, double* __restrict__ U, double* __restrict__ gc,
                                              double* __restrict__ cost)
 {
     const double* jl = camtab + (int64_t)c * CAM_STRIDE + CAM_JL;
-    const double j[9] = {jl[0], jl[1], jl[2], jl[3], jl[4], jl[5], jl[6], jl[7], jl[8]};
-    __syncwarp();
-    if (lane < 16) {  // columns 9..11 of row `lane`  <-  row * Jl
-        const double a0 = G[lane * NE_GLD + 9], a1 = G[lane * NE_GLD + 10], a2 = G[lane * NE_GLD + 11];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) G[lane * NE_GLD + 9 + i] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
-    }
-    __syncwarp();
-    if (lane < 16) {  // rows 9..11 of column `lane`  <-  Jl^T * column
-        const double a0 = G[9 * NE_GLD + lane], a1 = G[10 * NE_GLD + lane], a2 = G[11 * NE_GLD + lane];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) G[(9 + i) * NE_GLD + lane] = a0 * j[i] + a1 * j[3 + i] + a2 * j[6 + i];
-    }
     __syncwarp();
     double* Uc = U + (int64_t)c * 225;
-    for (int e = lane; e < 225; e += 32) {
-        const int a = e / 15, b = e - 15 * a;
-        atomicAdd(Uc + e, G[a * NE_GLD + b]);
+    for (int e = lane; e < 256; e += 32) {
+        const int a = e >> 4, b = e & 15;   // a, b = 15: the residual column
+        const bool ra = a >= 9 && a < 12, rb = b >= 9 && b < 12;
+        double v = 0.0;
+        if (!ra && !rb) {
+            v = cam_sum(G, a, b);
+        } else if (ra && !rb) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v += jl[3 * i + (a - 9)] * cam_sum(G, 9 + i, b);
+        } else if (!ra && rb) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v += cam_sum(G, a, 9 + i) * jl[3 * i + (b - 9)];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v += jl[3 * i + (a - 9)] * cam_sum(G, 9 + i, 9 + k) * jl[3 * k + (b - 9)];
+        }
+        if (a < 15 && b < 15) atomicAdd(Uc + a * 15 + b, v);
+        else if (a < 15) atomicAdd(gc + (int64_t)c * 15 + a, v);          // b == 15
+        else if (b == 15) atomicAdd(cost, v);                              // a == b == 15
     }
-    if (lane < 15) atomicAdd(gc + (int64_t)c * 15 + lane, G[lane * NE_GLD + 15]);
-    if (lane == 15) atomicAdd(cost, G[15 * NE_GLD + 15]);
     __syncwarp();
-    for (int e = lane; e < 16 * NE_GLD; e += 32) G[e] = 0.0;   // the sums restart with the next camera
+    for (int e = lane; e < 192; e += 32) G[e] = 0.0;   // the sums restart with the next camera
     __syncwarp();
 }
 
@@ -256,7 +269,7 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     double* const scratch = ws + 2 * NE_TILE_DOUBLES;   // Tbar: constant entries are written once
     scratch[lane] = 0.0;
     scratch[32 + lane] = lane == 30 ? 1.0 : 0.0;       // Tbar[7][6] = 1
-    for (int e = lane; e < 16 * NE_GLD; e += 32) scratch[64 + e] = 0.0;
+    for (int e = lane; e < 192; e += 32) scratch[64 + e] = 0.0;
     __syncwarp();
     int64_t cur_seg = sb - 1;   // segments are visited in order: a piece head advances this counter
     int cur_c = -1, cur_m = -1;
