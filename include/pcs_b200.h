@@ -196,6 +196,12 @@ PCS_API void pcs_lm_default_options(pcs_lm_options* o);
 PCS_API int pcs_lm_solve(pcs_problem* p, const double* x0 /*[n_free]*/, const pcs_lm_options* opts,
                          double* x_out /*[n_free]*/, pcs_lm_stats* stats);
 
+/* Dense symmetric positive definite solve S x = b with the persistent tiled Cholesky kernel that pcs_lm_solve uses for
+ * the reduced camera system (the counterpart of the LSMR solve inside scipy's TRF, optimisation_handling.py:88-98).
+ * Host buffers; A is column-major [n][n], only the lower triangle is read.  *info: 0 ok, 1 not positive definite.
+ * Exposed so that the solver kernel can be tested on its own. */
+PCS_API int pcs_spd_solve(int device, int64_t n, const double* A, const double* b, double* x /*[n]*/, int* info);
+
 /* Optional kernel timing: when enabled, every launch of the fused normal-equation kernel is bracketed by a pair of
  * CUDA events on the problem's stream (a ring of 1024 pairs, so a timed loop needs no synchronisation inside).
  * pcs_timing_get returns the duration (ms) of the most recent launch, pcs_timing_get_all the durations of the last

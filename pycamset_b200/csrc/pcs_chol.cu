@@ -1,0 +1,549 @@
+// pcs_chol.cu -- dense SPD solve  S x = b  of the reduced camera system, one persistent kernel.
+//
+// Replaces cusolverDnDpotrf + cusolverDnDpotrs in the LM step (the counterpart of the LSMR solve inside scipy's TRF,
+// optimisation_handling.py:88-98).  n = 15 C is small (480 at 32 cameras, 1920 at 128): the factorisation is a chain
+// of n dependent pivots, so what matters is the latency of one block step, not throughput.  cuSOLVER spends ~240 us in
+// potrf and ~90 us in the two triangular solves at n = 480; this kernel needs one grid barrier per 32-column block step:
+//
+//   * 32 x 32 tiles of the lower triangle, in place in global memory (L2-resident); b rides along as one more block
+//     row, so the forward substitution is part of the factorisation.
+//   * Phase k (k = 0 .. nb-1), separated by one grid barrier: every CTA that owns a tile of block column k rebuilds the
+//     diagonal tile itself -- A_kk minus the (lagged) rank-32 update with panel k-1 -- and factors it in one warp
+//     (row per lane, pivots broadcast by shuffles), so nobody waits for a "diagonal done" message; it then applies the
+//     lagged update to its own tile and solves it against L_kk^T.  Tiles right of the panel only get the lagged update.
+//   * After the last phase CTA 0 runs the back substitution  x = L^-T y  out of shared memory.
+// Tiles are assigned round-robin per phase, panel tiles first (one per CTA while the grid is wide enough).
+// The kernel is launched cooperatively (co-residency is required by the barrier); loads of data written by other
+// CTAs bypass L1 (ld.global.cg).
+#include <algorithm>
+
+#include "pcs_internal.cuh"
+
+namespace pcs {
+
+namespace {
+
+constexpr int TB = 32;               // tile edge
+constexpr int TP = 34;               // padded row length of a tile in shared memory (even: 16-byte aligned rows)
+constexpr int TILE_DOUBLES = TB * TP;
+constexpr int CHOL_THREADS = 128;
+constexpr int CH_WARPS = CHOL_THREADS / 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct CholProblem {
+    double* A;        // [n][ld] column-major, lower triangle
+    double* rhs;      // [n]
+    double* Ldiag;    // [nb][32 * 32] row-major
+    unsigned* bar;
+    int* info;
+    int64_t n, ld;
+    int nb;
+    long long* trace;   // optional [nb + 1][8] globaltimer stamps of CTA 0 (tools/chol_trace.cu), else nullptr
+};
+
+__device__ __forceinline__ void trace_stamp(const CholProblem& P, int k, int slot)
+{
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[k * 8 + slot] = t;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Shared-memory tiles are COLUMN-major, S[c * TP + r] = element (r, c): that is the layout of the matrix in global
+// memory, so a full tile moves with 16-byte asynchronous copies (two rows of one column per copy) and a factored
+// diagonal tile is at the same time L^T in row-major form (row j = column j of L, contiguous for tile_trsm).
+
+// element (r, c) of tile (bi, bj); bi == nb is the right-hand-side row.  Rows / columns past n are padded with the identity.
+__device__ __forceinline__ double tile_load(const CholProblem& P, int bi, int bj, int r, int c)
+{
+    const int64_t gc = (int64_t)TB * bj + c, gr = (int64_t)TB * bi + r;
+    const bool rhs_row = bi == P.nb;
+    const bool in = gc < P.n && (rhs_row ? r == 0 : gr < P.n);
+    const double* src = rhs_row ? P.rhs + gc : P.A + gc * P.ld + gr;
+    double v = (gc >= P.n && bi == bj && r == c) ? 1.0 : 0.0;
+    if (in) v = __ldcg(src);
+    return v;
+}
+
+__device__ __forceinline__ bool tile_is_full(const CholProblem& P, int bi, int bj)
+{
+    return bi < P.nb && (int64_t)TB * (bi + 1) <= P.n && (int64_t)TB * (bj + 1) <= P.n && (P.ld & 1) == 0;
+}
+
+// start fetching tile (bi, bj) into S; complete after cp_async_wait_all() + __syncthreads()
+__device__ __forceinline__ void tile_fetch(const CholProblem& P, int bi, int bj, double* __restrict__ S)
+{
+    if (tile_is_full(P, bi, bj)) {
+        const double* src = P.A + (int64_t)TB * bj * P.ld + (int64_t)TB * bi;
+#pragma unroll
+        for (int q = 0; q < (TB * TB / 2) / CHOL_THREADS; ++q) {
+            const int e = threadIdx.x + q * CHOL_THREADS, c = e >> 4, r = (e & 15) * 2;
+            cp_async16(S + c * TP + r, src + (int64_t)c * P.ld + r);
+        }
+    } else {
+        // ragged tiles and the right-hand-side row: all guarded loads first (one round trip), then the stores
+        const int r = threadIdx.x & 31, c0 = threadIdx.x >> 5;
+        double v[TB / CH_WARPS];
+#pragma unroll
+        for (int q = 0; q < TB / CH_WARPS; ++q) v[q] = tile_load(P, bi, bj, r, c0 + q * CH_WARPS);
+#pragma unroll
+        for (int q = 0; q < TB / CH_WARPS; ++q) S[(c0 + q * CH_WARPS) * TP + r] = v[q];
+    }
+}
+
+__device__ __forceinline__ void tile_store(const CholProblem& P, int bi, int bj, const double* __restrict__ S)
+{
+    if (tile_is_full(P, bi, bj)) {
+        double* dst = P.A + (int64_t)TB * bj * P.ld + (int64_t)TB * bi;
+#pragma unroll
+        for (int q = 0; q < (TB * TB / 2) / CHOL_THREADS; ++q) {
+            const int e = threadIdx.x + q * CHOL_THREADS, c = e >> 4, r = (e & 15) * 2;
+            *reinterpret_cast<double2*>(dst + (int64_t)c * P.ld + r) = *reinterpret_cast<const double2*>(S + c * TP + r);
+        }
+        return;
+    }
+    const int r = threadIdx.x & 31;
+    for (int c = threadIdx.x >> 5; c < TB; c += CHOL_THREADS / 32) {
+        const int64_t gc = (int64_t)TB * bj + c;
+        if (gc >= P.n) continue;
+        if (bi == P.nb) { if (r == 0) P.rhs[gc] = S[c * TP]; continue; }
+        const int64_t gr = (int64_t)TB * bi + r;
+        if (gr < P.n) P.A[gc * P.ld + gr] = S[c * TP + r];
+    }
+}
+
+// T -= X Y^T (32 x 32 tiles in shared memory) by warps [W0, W0 + NW) of the CTA, NW = 4 or 3.  A thread owns row r and
+// a contiguous, even-aligned block of columns (8 each for four warps; 12 / 10 / 10 for three), so the Y operand
+// arrives with 16-byte broadcast loads; one accumulation chain per column keeps the FP64 pipe fed.
+template <int W0, int NW>
+__device__ __forceinline__ void tile_update(double* __restrict__ T, const double* __restrict__ X, const double* __restrict__ Y)
+{
+    static_assert(NW == 4 || NW == 3, "column blocks are laid out for 3 or 4 warps");
+    const int r = threadIdx.x & 31, w = (int)(threadIdx.x >> 5) - W0;
+    if (w < 0 || w >= NW) return;
+    constexpr int NP = NW == 4 ? 4 : 6;                       // column pairs per thread (upper bound)
+    const int c_lo = NW == 4 ? 8 * w : (w == 0 ? 0 : 2 + 10 * w);
+    const int np = NW == 4 ? 4 : (w == 0 ? 6 : 5);
+    double acc[2 * NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        acc[2 * q] = q < np ? T[(c_lo + 2 * q) * TP + r] : 0.0;
+        acc[2 * q + 1] = q < np ? T[(c_lo + 2 * q + 1) * TP + r] : 0.0;
+    }
+#pragma unroll 4
+    for (int t = 0; t < TB; ++t) {
+        const double x = X[t * TP + r];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (q < np) {
+                const double2 y = *reinterpret_cast<const double2*>(Y + t * TP + c_lo + 2 * q);
+                acc[2 * q] = fma(-x, y.x, acc[2 * q]);
+                acc[2 * q + 1] = fma(-x, y.y, acc[2 * q + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        if (q < np) {
+            T[(c_lo + 2 * q) * TP + r] = acc[2 * q];
+            T[(c_lo + 2 * q + 1) * TP + r] = acc[2 * q + 1];
+        }
+    }
+}
+
+__device__ __forceinline__ double lds_f64(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_v2f64(unsigned addr, double& x, double& y)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+
+// branch-free reciprocal: MUFU.RCP64H seed (~20 bits) + two Newton steps (full double accuracy for normal arguments)
+__device__ __forceinline__ double rcp_newton(double d)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
+// Cholesky of the 32 x 32 tile D (shared memory, column-major) by one warp, lane r = row r.
+//   * The elimination runs in the square-root-free form (A = L' diag(d) L'^T); the 32 inverse square roots that turn
+//     L' into the Cholesky factor are taken afterwards, off the dependent chain.
+//   * Every lane tracks the pivot sequence itself: d_{j+1} = a'_{j+1,j+1} - u_{j+1,j}^2 / d_j, where a' (the diagonal
+//     entry before step j) is fetched by a shuffle issued one step early and u comes from the column broadcast -- the
+//     chain of a step is one reciprocal and one FMA, no shuffle, no compare.
+//   * The column of step j reaches the other lanes through a double-buffered shared-memory vector.
+// Results: D <- L (column-major, upper part zeroed), invd[j] = 1 / L_jj.  Returns false if a pivot is not positive.
+__device__ __forceinline__ bool tile_factor(double* __restrict__ D, double* __restrict__ invd, double* __restrict__ colbuf /*[2][32]*/,
+                                            int lane)
+{
+    double a[TB];
+#pragma unroll
+    for (int c = 0; c < TB; ++c) a[c] = D[c * TP + lane];
+    bool ok = true;
+    const unsigned cb_addr = (unsigned)__cvta_generic_to_shared(colbuf);
+    double d = __shfl_sync(FULL, a[0], 0);        // pivot 0
+    colbuf[lane] = a[0];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < TB; ++j) {
+        // column j, unscaled (cb[r] = a_rj), pulled into registers in one batch at the top of the step: issued through
+        // volatile asm so that the loads stay ahead of the reciprocal chain instead of trickling in front of their uses
+        const unsigned cb = cb_addr + (j & 1) * TB * 8;
+        double cbv[TB];
+        if ((j + 1) & 1) { if (j + 1 < TB) cbv[j + 1] = lds_f64(cb + (j + 1) * 8); }
+#pragma unroll
+        for (int c = (j + 2) & ~1; c < TB; c += 2) lds_v2f64(cb + c * 8, cbv[c], cbv[c + 1]);
+        __syncwarp();                              // scheduling fence: keeps the batch of loads above the arithmetic
+        ok = ok && (d > 0.0);
+        if (lane == 0) invd[j] = d;                // pivots, turned into 1 / sqrt below
+        const double inv = rcp_newton(d);
+        if (j + 1 < TB) {
+            // next pivot, on every lane: a'_{j+1,j+1} (before this step's update) - u^2 inv
+            const double apd = __shfl_sync(FULL, a[j + 1], j + 1);
+            const double u = cbv[j + 1];
+            d = fma(-(u * u), inv, apd);
+        }
+        const double w = a[j] * inv;
+#pragma unroll
+        for (int c = j + 1; c < TB; ++c) a[c] = fma(-w, cbv[c], a[c]);
+        if (j + 1 < TB) {
+            colbuf[((j + 1) & 1) * TB + lane] = a[j + 1];
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    const double rs = rsqrt(invd[lane]);           // lane j: 1 / sqrt(d_j)
+    __syncwarp();
+    invd[lane] = rs;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < TB; ++c) D[c * TP + lane] = c <= lane ? a[c] * invd[c] : 0.0;
+    return ok;
+}
+
+// X <- X L^-T for the 32 rows of tile T (shared memory), one row per lane; L (column-major: row j of the buffer is
+// column j of L) and invd in shared memory
+__device__ __forceinline__ void tile_trsm(double* __restrict__ T, const double* __restrict__ L, const double* __restrict__ invd, int lane)
+{
+    double x[TB];
+#pragma unroll
+    for (int c = 0; c < TB; ++c) x[c] = T[c * TP + lane];
+#pragma unroll
+    for (int j = 0; j < TB; ++j) {
+        const double xj = x[j] * invd[j];
+        x[j] = xj;
+        const double* col = L + j * TP;      // col[c] = L[c][j]
+        if (!(j & 1)) x[j + 1] = fma(-xj, col[j + 1], x[j + 1]);
+#pragma unroll
+        for (int c = (j + 2) & ~1; c < TB; c += 2) {
+            const double2 l = *reinterpret_cast<const double2*>(col + c);
+            x[c] = fma(-xj, l.x, x[c]);
+            x[c + 1] = fma(-xj, l.y, x[c + 1]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < TB; ++c) T[c * TP + lane] = x[c];
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* info)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        int spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target && ++spins < (1 << 24));
+        if (v < target) *info = -2;   // a CTA never arrived: give up instead of hanging the device
+    }
+    __syncthreads();
+}
+
+// tile t of phase k: panel tiles (i, k), i = k+1 .. nb first, then the trailing tiles (i, j), k < j <= i <= nb, (nb, nb) excluded
+__device__ __forceinline__ void phase_tile(int k, int nb, int t, int& bi, int& bj)
+{
+    const int n_panel = nb - k;
+    if (t < n_panel) { bi = k + 1 + t; bj = k; return; }
+    t -= n_panel;
+    // trailing: rows i = k+1 .. nb, columns j = k+1 .. min(i, nb-1)
+    for (int i = k + 1; i <= nb; ++i) {
+        const int w = ::min(i, nb - 1) - k;
+        if (t < w) { bi = i; bj = k + 1 + t; return; }
+        t -= w;
+    }
+    bi = -1; bj = -1;
+}
+
+constexpr int RB_STRIDE = TB + 2;   // row-block buffer of the back substitution: column c at RB + c * RB_STRIDE
+
+__global__ void __launch_bounds__(CHOL_THREADS)
+k_chol_solve(CholProblem P)
+{
+    extern __shared__ __align__(16) double ch_smem[];
+    double* D = ch_smem;                       // diagonal tile / L_kk
+    double* Pk = D + TILE_DOUBLES;             // L_{k,k-1}
+    double* T = Pk + TILE_DOUBLES;             // the tile being processed
+    double* X = T + TILE_DOUBLES;              // L_{i,k-1}
+    double* Y = X + TILE_DOUBLES;              // L_{j,k-1}
+    double* invd = Y + TILE_DOUBLES;           // [32]
+    double* colbuf = invd + TB;                // [2][32]
+    double* yv = colbuf + 2 * TB;              // [nb * 32] back substitution (CTA 0)
+    double* RB = yv + P.nb * TB;               // [(nb - 1) * 32][RB_STRIDE] row block of L (CTA 0)
+    __shared__ int s_bad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = P.nb;
+    if (threadIdx.x == 0) s_bad = 0;
+
+    for (int k = 0; k < nb; ++k) {
+        const int n_panel = nb - k;
+        int n_tiles = n_panel;
+        if (k > 0)   // phase 0 has no lagged update: only the panel is touched
+            for (int i = k + 1; i <= nb; ++i) n_tiles += ::min(i, nb - 1) - k;
+        const bool has_panel = (int)blockIdx.x < n_panel;     // then this CTA's first tile is the panel tile (k + 1 + blockIdx, k)
+        trace_stamp(P, k, 0);
+        int t_next = blockIdx.x;
+        if (has_panel) {
+            // all global loads of the critical path are issued together: diagonal tile, L_{k,k-1}, the panel tile and its L_{i,k-1}
+            const int bi = k + 1 + (int)blockIdx.x;
+            tile_fetch(P, k, k, D);
+            if (k > 0) tile_fetch(P, k, k - 1, Pk);
+            tile_fetch(P, bi, k, T);
+            if (k > 0) tile_fetch(P, bi, k - 1, X);
+            cp_async_wait_all();
+            __syncthreads();
+            trace_stamp(P, k, 5);
+            if (k > 0) tile_update<0, CH_WARPS>(D, Pk, Pk);            // the diagonal tile, rebuilt locally (lagged update)
+            __syncthreads();
+            trace_stamp(P, k, 1);
+            if (warp == 0) {                                           // warp 0 factors it ...
+                const long long c0 = clock64();
+                if (!tile_factor(D, invd, colbuf, lane) && lane == 0) s_bad = 1;
+                if (P.trace && blockIdx.x == 0 && lane == 0) P.trace[k * 8 + 7] = clock64() - c0;   // cycles
+            } else if (k > 0) {
+                tile_update<1, CH_WARPS - 1>(T, X, Pk);                // ... while the others bring the panel tile up to date
+            }
+            __syncthreads();
+            trace_stamp(P, k, 2);
+            if (warp == 0) tile_trsm(T, D, invd, lane);
+            else if (blockIdx.x == 0)                                  // L_kk for the back substitution, row-major
+                for (int e = threadIdx.x - 32; e < TB * TB; e += CHOL_THREADS - 32) P.Ldiag[(int64_t)k * TB * TB + e] = D[(e & 31) * TP + (e >> 5)];
+            __syncthreads();
+            trace_stamp(P, k, 6);
+            tile_store(P, bi, k, T);
+            __syncthreads();
+            t_next += gridDim.x;
+        } else {
+            trace_stamp(P, k, 5);
+            trace_stamp(P, k, 1);
+            trace_stamp(P, k, 2);
+            trace_stamp(P, k, 6);
+        }
+        for (int t = t_next; t < n_tiles; t += gridDim.x) {
+            int bi, bj;
+            phase_tile(k, nb, t, bi, bj);
+            const bool panel = bj == k;   // only when the grid is narrower than the panel
+            tile_fetch(P, bi, bj, T);
+            if (k > 0) { tile_fetch(P, bi, k - 1, X); if (!panel) tile_fetch(P, bj, k - 1, Y); }
+            cp_async_wait_all();
+            __syncthreads();
+            if (k > 0) tile_update<0, CH_WARPS>(T, X, panel ? Pk : Y);
+            __syncthreads();
+            if (panel) {
+                if (warp == 0) tile_trsm(T, D, invd, lane);
+                __syncthreads();
+            }
+            tile_store(P, bi, bj, T);
+            __syncthreads();
+        }
+        trace_stamp(P, k, 3);
+        grid_barrier(P.bar, (unsigned)(k + 1) * gridDim.x, P.info);
+        trace_stamp(P, k, 4);
+    }
+    if (blockIdx.x != 0) return;
+    if (threadIdx.x == 0 && s_bad) *P.info = 1;
+
+    // Back substitution x = L^-T y by CTA 0.  Step k: warp 0 solves L_kk^T x_k = y_k (Ldiag block k, row-major, fetched
+    // one step ahead) while row block k of L (32 x 32 k) streams into shared memory; then every thread owns columns of
+    // that block and subtracts its share from y.
+    trace_stamp(P, nb, 0);
+    for (int e = threadIdx.x; e < nb * TB; e += CHOL_THREADS) yv[e] = e < P.n ? __ldcg(P.rhs + e) : 0.0;
+    for (int e = threadIdx.x; e < TB * (TB / 2); e += CHOL_THREADS) {
+        const int r = e >> 4, c = (e & 15) * 2;
+        cp_async16(D + r * TP + c, P.Ldiag + (int64_t)(nb - 1) * TB * TB + r * TB + c);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int k = nb - 1; k >= 0; --k) {
+        double* cur = ((nb - 1 - k) & 1) ? Pk : D;
+        double* nxt = ((nb - 1 - k) & 1) ? D : Pk;
+        const int rows = (int)::min((long long)TB, (long long)(P.n - (int64_t)TB * k));
+        const int ncol = k * TB;
+        // row block k of L into shared memory, RB[c][r] = L[32 k + r][c], and the next diagonal block: asynchronous
+        // 16-byte copies when the addresses allow it (even leading dimension, full block), guarded loads otherwise
+        const bool fast = (P.ld % 2 == 0) && rows == TB;
+        if (fast) {
+            for (int e = threadIdx.x; e < ncol * (TB / 2); e += CHOL_THREADS) {
+                const int c = e >> 4, r = (e & 15) * 2;
+                cp_async16(RB + c * RB_STRIDE + r, P.A + (int64_t)c * P.ld + (int64_t)TB * k + r);
+            }
+        }
+        if (k > 0)
+            for (int e = threadIdx.x; e < TB * (TB / 2); e += CHOL_THREADS) {
+                const int r = e >> 4, c = (e & 15) * 2;
+                cp_async16(nxt + r * TP + c, P.Ldiag + (int64_t)(k - 1) * TB * TB + r * TB + c);
+            }
+        if (warp == 0) {
+            double yc = yv[k * TB + lane];
+            double lcol[TB];                    // column `lane` of L_kk: lcol[r] = L[r][lane]
+#pragma unroll
+            for (int r = 0; r < TB; ++r) lcol[r] = cur[r * TP + lane];
+            __syncwarp();                       // scheduling fence (see tile_factor)
+            const double inv = rcp_newton(cur[lane * TP + lane]);
+#pragma unroll
+            for (int r = TB - 1; r >= 0; --r) {
+                const double xr = __shfl_sync(FULL, yc * inv, r);
+                if (lane == r) yc = xr;
+                else if (lane < r) yc = fma(-lcol[r], xr, yc);
+            }
+            yv[k * TB + lane] = yc;
+        } else if (!fast) {
+            for (int e0 = threadIdx.x - 32; e0 < ncol * TB; e0 += 8 * (CHOL_THREADS - 32)) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * (CHOL_THREADS - 32);
+                    const int c = e >> 5, r = e & 31;
+                    v[u] = (e < ncol * TB && r < rows) ? __ldcg(P.A + (int64_t)c * P.ld + (int64_t)TB * k + r) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * (CHOL_THREADS - 32);
+                    if (e < ncol * TB) RB[(e >> 5) * RB_STRIDE + (e & 31)] = v[u];
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (threadIdx.x < ncol) {
+            double xk[TB];
+#pragma unroll
+            for (int r = 0; r < TB; r += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(yv + k * TB + r);
+                xk[r] = v.x; xk[r + 1] = v.y;
+            }
+            for (int c = threadIdx.x; c < ncol; c += CHOL_THREADS) {
+                const double* col = RB + c * RB_STRIDE;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int r = 0; r < TB; r += 4) {
+                    const double2 l0 = *reinterpret_cast<const double2*>(col + r);
+                    const double2 l1 = *reinterpret_cast<const double2*>(col + r + 2);
+                    s0 = fma(l0.x, xk[r], s0);
+                    s1 = fma(l0.y, xk[r + 1], s1);
+                    s2 = fma(l1.x, xk[r + 2], s2);
+                    s3 = fma(l1.y, xk[r + 3], s3);
+                }
+                yv[c] -= (s0 + s1) + (s2 + s3);
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < P.n; e += CHOL_THREADS) P.rhs[e] = yv[e];
+    trace_stamp(P, nb, 1);
+}
+
+size_t chol_smem_bytes(int nb)
+{
+    return (size_t)(5 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)std::max(nb - 1, 0) * TB * RB_STRIDE) * sizeof(double);
+}
+
+}  // namespace
+
+// Workspace + launch geometry.  grid = 0 on return means "not usable here" (caller falls back to cuSOLVER).
+int chol_prepare(int device, int64_t n, double** Ldiag, unsigned** bar, int* grid)
+{
+    *grid = 0;
+    const int nb = (int)((n + TB - 1) / TB);
+    const size_t smem = chol_smem_bytes(nb);
+    int max_optin = 0, sms = 0, coop = 0;
+    PCS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    PCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    PCS_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop || smem > (size_t)max_optin) return PCS_OK;
+    PCS_CUDA(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_solve, CHOL_THREADS, smem));
+    if (per_sm < 1) return PCS_OK;
+    const int n_tiles0 = nb + nb * (nb + 1) / 2;   // upper bound of the tiles of a phase
+    PCS_CUDA(cudaMalloc((void**)Ldiag, (size_t)nb * TB * TB * sizeof(double)));
+    PCS_CUDA(cudaMalloc((void**)bar, sizeof(unsigned)));
+    *grid = std::max(1, std::min(sms, n_tiles0));
+    return PCS_OK;
+}
+
+int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t ld, double* rhs, double* Ldiag, unsigned* bar,
+                      int* info, long long* trace)
+{
+    CholProblem P;
+    P.trace = trace;
+    P.A = A; P.rhs = rhs; P.Ldiag = Ldiag; P.bar = bar; P.info = info; P.n = n; P.ld = ld;
+    P.nb = (int)((n + TB - 1) / TB);
+    PCS_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    PCS_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    void* args[] = {&P};
+    PCS_CUDA(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_THREADS), args, chol_smem_bytes(P.nb), st));
+    return PCS_OK;
+}
+
+}  // namespace pcs
+
+extern "C" int pcs_spd_solve(int device, int64_t n, const double* A, const double* b, double* x, int* info)
+{
+    using namespace pcs;
+    PCS_REQUIRE(n > 0 && A && b && x, "NULL argument or n <= 0");
+    PCS_CUDA(cudaSetDevice(device));
+    double *dA = nullptr, *db = nullptr, *Ldiag = nullptr;
+    unsigned* bar = nullptr;
+    int* dinfo = nullptr;
+    int grid = 0;
+    int rc = chol_prepare(device, n, &Ldiag, &bar, &grid);
+    if (rc == PCS_OK && grid == 0) { set_error("pcs_spd_solve: n too large for the persistent kernel on this device"); rc = PCS_ERR_UNSUPPORTED; }
+    auto cleanup = [&]() { cudaFree(dA); cudaFree(db); cudaFree(Ldiag); cudaFree(bar); cudaFree(dinfo); };
+    if (rc != PCS_OK) { cleanup(); return rc; }
+    cudaError_t e = cudaMalloc((void**)&dA, (size_t)(n * n) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&db, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dinfo, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(dA, A, (size_t)(n * n) * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, (size_t)n * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error(std::string("pcs_spd_solve: ") + cudaGetErrorString(e)); cleanup(); return PCS_ERR_CUDA; }
+    rc = launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, dinfo);
+    int h_info = 0;
+    if (rc == PCS_OK) {
+        e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(x, db, (size_t)n * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&h_info, dinfo, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error(std::string("pcs_spd_solve: ") + cudaGetErrorString(e)); rc = PCS_ERR_CUDA; }
+    }
+    if (info) *info = h_info;
+    cleanup();
+    if (rc == PCS_OK && h_info != 0) { set_error("pcs_spd_solve: matrix is not positive definite"); rc = PCS_ERR_NUMERIC; }
+    return rc;
+}

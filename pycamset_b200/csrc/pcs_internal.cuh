@@ -116,5 +116,9 @@ int launch_cost_only(pcs_problem* p, double* cost_dev);
 int launch_normal_blocks(pcs_problem* p, bool targets_cleared = false, int part = 0, int n_parts = 1);
 int ensure_pinned(pcs_problem* p, int64_t doubles);
 void lm_free(pcs_problem* p);
+// pcs_chol.cu: dense SPD solve of the reduced camera system in one persistent kernel
+int chol_prepare(int device, int64_t n, double** Ldiag, unsigned** bar, int* grid);
+int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t ld, double* rhs, double* Ldiag, unsigned* bar,
+                      int* info, long long* trace = nullptr);
 void p2p_free(pcs_problem* p);
 }  // namespace pcs

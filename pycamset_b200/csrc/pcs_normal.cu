@@ -245,7 +245,71 @@ __device__ __forceinline__ void gram_step(NeAcc& S, const double* __restrict__ w
     dmma884(S.bb[0], S.bb[1], v1, v1);
 }
 
-template <int CTAS_PER_SM, int WARPS>
+// Streamed observation loads: every observation is read exactly once per evaluation, so the loads bypass L1
+// allocation and leave the (small) L1 that remains beside the staging buffers to the camera / pose / template rows.
+__device__ __forceinline__ int ld_stream(const int32_t* p)
+{
+    int v;
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p)
+{
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// One observation's inputs (sorted layout); c < 0 marks a lane past the end of the warp's range.
+struct NeObs {
+    int c, m, k;
+    double2 uv;
+};
+__device__ __forceinline__ void load_obs(NeObs& o, int64_t i, int64_t end, const int32_t* __restrict__ s_cam,
+                                         const int32_t* __restrict__ s_pose, const int32_t* __restrict__ s_key,
+                                         const double2* __restrict__ s_uv)
+{
+    if (i < end) { o.c = ld_stream(s_cam + i); o.m = ld_stream(s_pose + i); o.k = ld_stream(s_key + i); o.uv = ld_stream(s_uv + i); }
+    else { o.c = -1; o.m = -1; }
+}
+
+// Evaluated rows of one observation, as staged: tile 0 = [xD 1 0 0 Au0..3] / [0 0 yD 1 Av0..3],
+// tile 1 = [Au4 Wc Pm r] per image row.
+struct NeRows {
+    double xD, yD, Au[5], Av[5], Pm[6], Wc[6], res[2];
+};
+__device__ __forceinline__ void eval_rows(const NeObs& o, const double* __restrict__ camtab, const double* __restrict__ posetab,
+                                          const double* __restrict__ pts, NeRows& R)
+{
+    // lanes past the end evaluate row 0 of every table (never staged)
+    const double* ct = camtab + (int64_t)max(o.c, 0) * CAM_STRIDE;
+    const double* ptab = posetab + (int64_t)max(o.m, 0) * POSE_STRIDE;
+    ObsJacCam J;
+    eval_obs_cam(ct, ptab, pts + 4 * (int64_t)(o.c < 0 ? 0 : o.k), o.uv.x, o.uv.y, R.res, J);
+    R.xD = J.xD; R.yD = J.yD;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { R.Au[i] = J.Au[i]; R.Av[i] = J.Av[i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { R.Pm[i] = J.Pm[i]; R.Wc[i] = J.Wc[i]; }
+}
+__device__ __forceinline__ void stage_rows(const NeRows& R, double* __restrict__ st_u, double* __restrict__ st_v, int st_rot)
+{
+    {
+        const double t0[8] = {R.xD, 1.0, 0.0, 0.0, R.Au[0], R.Au[1], R.Au[2], R.Au[3]};
+        const double t1[8] = {R.Au[4], R.Wc[0], R.Wc[1], R.Wc[2], R.Pm[0], R.Pm[1], R.Pm[2], R.res[0]};
+        stage_store_row(st_u, st_rot, t0, t1);
+    }
+    {
+        const double t0[8] = {0.0, 0.0, R.yD, 1.0, R.Av[0], R.Av[1], R.Av[2], R.Av[3]};
+        const double t1[8] = {R.Av[4], R.Wc[3], R.Wc[4], R.Wc[5], R.Pm[3], R.Pm[4], R.Pm[5], R.res[1]};
+        stage_store_row(st_v, st_rot, t0, t1);
+    }
+}
+
+// OPL = observations per lane and loop trip.  With OPL = 2 a lane evaluates two observations back to back (two
+// independent dependency chains: the evaluation phase is latency-bound, not issue-bound) and the warp then runs the
+// staging + Gram phase once per half, re-using the one 8 KB staging buffer.
+template <int CTAS_PER_SM, int WARPS, int OPL>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
 k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_pose,
          const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv, const int64_t* __restrict__ seg_start,
@@ -282,90 +346,84 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     const int g8 = lane >> 2, jb = (lane >> 1) & 1, jr = lane & 1;
     const int ld_L = 16 * jb + 8 * jr + (g8 ^ (4 * jb));
 
-    // software prefetch: the inputs of the next batch are requested before the current batch is evaluated
-    int c_n = -1, m_n = -1, k_n = 0;
-    double2 uv_n = make_double2(0.0, 0.0);
-    if (begin + lane < end) {
-        c_n = s_cam[begin + lane]; m_n = s_pose[begin + lane]; k_n = s_key[begin + lane]; uv_n = s_uv[begin + lane];
-    }
+    // software prefetch: the inputs of the next trip are requested before the current trip is evaluated
+    NeObs nxt[OPL];
+#pragma unroll
+    for (int h = 0; h < OPL; ++h) load_obs(nxt[h], begin + 32 * h + lane, end, s_cam, s_pose, s_key, s_uv);
 
-    for (int64_t base = begin; base < end; base += 32) {
-        const int cnt = (int)min((int64_t)32, end - base);
-        const int c = c_n, m = m_n, k = k_n;
-        const double2 o = uv_n;
-        {
-            const int64_t i = base + 32 + lane;
-            if (i < end) { c_n = s_cam[i]; m_n = s_pose[i]; k_n = s_key[i]; uv_n = s_uv[i]; }
-        }
-        if (lane < cnt) {
-            const double* ct = camtab + (int64_t)c * CAM_STRIDE;
-            const double* ptab = posetab + (int64_t)m * POSE_STRIDE;
-            double res[2];
-            ObsJacCam J;
-            eval_obs_cam(ct, ptab, pts + 4 * (int64_t)k, o.x, o.y, res, J);
-            {
-                const double t0[8] = {J.xD, 1.0, 0.0, 0.0, J.Au[0], J.Au[1], J.Au[2], J.Au[3]};
-                const double t1[8] = {J.Au[4], J.Wc[0], J.Wc[1], J.Wc[2], J.Pm[0], J.Pm[1], J.Pm[2], res[0]};
-                stage_store_row(st_u, st_rot, t0, t1);
-            }
-            {
-                const double t0[8] = {0.0, 0.0, J.yD, 1.0, J.Av[0], J.Av[1], J.Av[2], J.Av[3]};
-                const double t1[8] = {J.Av[4], J.Wc[3], J.Wc[4], J.Wc[5], J.Pm[3], J.Pm[4], J.Pm[5], res[1]};
-                stage_store_row(st_v, st_rot, t0, t1);
-            }
-        }
-        // the next batch's pose row (new for every segment) is pulled into L1 while this batch's Gram phase runs
-        if (m_n >= 0) {
-            const double* nx = posetab + (int64_t)m_n * POSE_STRIDE;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
-        }
-        // piece heads: lanes whose (camera, pose) differs from the previous observation's
-        int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
-        if (lane == 0) { pc = last_c; pm = last_m; }
-        const unsigned heads = __ballot_sync(0xffffffffu, lane < cnt && (c != pc || m != pm));
-        last_c = __shfl_sync(0xffffffffu, c, cnt - 1);
-        last_m = __shfl_sync(0xffffffffu, m, cnt - 1);
-        __syncwarp();
-        unsigned pieces = heads | 1u;  // a batch may start in the middle of a segment
-        while (pieces) {
-            const int a = __ffs(pieces) - 1;
-            pieces &= pieces - 1;
-            const int b = pieces ? __ffs(pieces) - 1 : cnt;
-            if ((heads >> a) & 1u) {
-                if (cur_c >= 0) flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
-                const int nc = __shfl_sync(0xffffffffu, c, a);
-                if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
-                ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
-            }
-            // k-steps of the piece: boundary steps shared with a neighbouring piece (odd a / odd b) are masked,
-            // interior steps run unmasked in groups of four with their fragment loads hoisted
-            int ks = a >> 1;
-            const int k1 = (b - 1) >> 1;
-            if (a & 1) {
-                gram_step<true>(S, ws, ld_L, ks, jb, a, b);
-                ++ks;
-            }
-            const int k_full = (b & 1) ? k1 : k1 + 1;   // first step that needs the tail mask (or one past the end)
-            for (; ks + 4 <= k_full; ks += 4) {
-                double v0[4], v1[4];
+    for (int64_t base = begin; base < end; base += 32 * OPL) {
+        NeObs ob[OPL];
+        NeRows rows[OPL];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double* f = ws + 32 * (ks + u) + (ld_L ^ ((((ks + u) & 1) << 3) | ((ks + u) & 2)));
-                    v0[u] = f[0];
-                    v1[u] = f[NE_TILE_DOUBLES];
-                }
+        for (int h = 0; h < OPL; ++h) ob[h] = nxt[h];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    dmma884(S.aa[0], S.aa[1], v0[u], v0[u]);
-                    dmma884(S.ab[0], S.ab[1], v0[u], v1[u]);
-                    dmma884(S.bb[0], S.bb[1], v1[u], v1[u]);
-                }
+        for (int h = 0; h < OPL; ++h) load_obs(nxt[h], base + 32 * (OPL + h) + lane, end, s_cam, s_pose, s_key, s_uv);
+#pragma unroll
+        for (int h = 0; h < OPL; ++h) eval_rows(ob[h], camtab, posetab, pts, rows[h]);
+        // the next trip's pose rows (new for every segment) are pulled into L1 while this trip's Gram phases run
+#pragma unroll
+        for (int h = 0; h < OPL; ++h)
+            if (nxt[h].m >= 0) {
+                const double* nx = posetab + (int64_t)nxt[h].m * POSE_STRIDE;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
             }
-            for (; ks < k_full; ++ks) gram_step<false>(S, ws, ld_L, ks, jb, a, b);
-            if (ks <= k1) gram_step<true>(S, ws, ld_L, ks, jb, a, b);
+#pragma unroll 1
+        for (int h = 0; h < OPL; ++h) {
+            const int cnt = (int)min((int64_t)32, end - base - 32 * h);
+            if (cnt <= 0) break;
+            const int c = (OPL > 1 && h) ? ob[OPL - 1].c : ob[0].c, m = (OPL > 1 && h) ? ob[OPL - 1].m : ob[0].m;
+            if (lane < cnt) {
+                if (OPL > 1 && h) stage_rows(rows[OPL - 1], st_u, st_v, st_rot);
+                else stage_rows(rows[0], st_u, st_v, st_rot);
+            }
+            // piece heads: lanes whose (camera, pose) differs from the previous observation's
+            int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
+            if (lane == 0) { pc = last_c; pm = last_m; }
+            const unsigned heads = __ballot_sync(0xffffffffu, lane < cnt && (c != pc || m != pm));
+            last_c = __shfl_sync(0xffffffffu, c, cnt - 1);
+            last_m = __shfl_sync(0xffffffffu, m, cnt - 1);
+            __syncwarp();
+            unsigned pieces = heads | 1u;  // a batch may start in the middle of a segment
+            while (pieces) {
+                const int a = __ffs(pieces) - 1;
+                pieces &= pieces - 1;
+                const int b = pieces ? __ffs(pieces) - 1 : cnt;
+                if ((heads >> a) & 1u) {
+                    if (cur_c >= 0) flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
+                    const int nc = __shfl_sync(0xffffffffu, c, a);
+                    if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
+                    ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
+                }
+                // k-steps of the piece: boundary steps shared with a neighbouring piece (odd a / odd b) are masked,
+                // interior steps run unmasked in groups of four with their fragment loads hoisted
+                int ks = a >> 1;
+                const int k1 = (b - 1) >> 1;
+                if (a & 1) {
+                    gram_step<true>(S, ws, ld_L, ks, jb, a, b);
+                    ++ks;
+                }
+                const int k_full = (b & 1) ? k1 : k1 + 1;   // first step that needs the tail mask (or one past the end)
+                for (; ks + 4 <= k_full; ks += 4) {
+                    double v0[4], v1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double* f = ws + 32 * (ks + u) + (ld_L ^ ((((ks + u) & 1) << 3) | ((ks + u) & 2)));
+                        v0[u] = f[0];
+                        v1[u] = f[NE_TILE_DOUBLES];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        dmma884(S.aa[0], S.aa[1], v0[u], v0[u]);
+                        dmma884(S.ab[0], S.ab[1], v0[u], v1[u]);
+                        dmma884(S.bb[0], S.bb[1], v1[u], v1[u]);
+                    }
+                }
+                for (; ks < k_full; ++ks) gram_step<false>(S, ws, ld_L, ks, jb, a, b);
+                if (ks <= k1) gram_step<true>(S, ws, ld_L, ks, jb, a, b);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     if (cur_c >= 0) {
         flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
@@ -429,12 +487,11 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
         PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
     }
     if (p->N == 0) return PCS_OK;
-    // occupancy variants (PCS_NE_CFG for A/B runs): 3 = 5 CTAs x 4 warps, 96 registers, no spills (default, 20 warps/SM:
-    // the shared-memory limit at 10.9 KB per warp), 0 = 4 CTAs x 4 warps (124 registers), 1 = 3 CTAs x 6 warps (96),
-    // 2 = 3 CTAs x 4 warps (142).  Measured on config 4: 0.132 / 0.138 / 0.144 / 0.149 ms.
-    static const int cfg = [] { const char* e = std::getenv("PCS_NE_CFG"); return e && e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 3; }();
-    const int ctas = cfg == 0 ? 4 : cfg == 3 ? 5 : 3, warps = cfg == 1 ? 6 : 4;
-    auto kern = cfg == 0 ? k_normal<4, 4> : cfg == 1 ? k_normal<3, 6> : cfg == 2 ? k_normal<3, 4> : k_normal<5, 4>;
+    // variants (PCS_NE_CFG for A/B runs): 3 = 5 CTAs x 4 warps, one observation per lane (96 registers);
+    // 0 = 4 CTAs x 4 warps, one per lane (128 registers); 4 = 4 CTAs x 4 warps, two per lane; 5 = 3 CTAs x 4 warps, two per lane.
+    static const int cfg = [] { const char* e = std::getenv("PCS_NE_CFG"); return e && e[0] >= '0' && e[0] <= '5' ? e[0] - '0' : 3; }();
+    const int ctas = cfg == 3 ? 5 : cfg == 5 ? 3 : 4, warps = 4, opl = cfg >= 4 ? 2 : 1;
+    auto kern = cfg == 0 ? k_normal<4, 4, 1> : cfg == 4 ? k_normal<4, 4, 2> : cfg == 5 ? k_normal<3, 4, 2> : k_normal<5, 4, 1>;
     static bool attr_set = false;
     const size_t smem = (size_t)warps * NE_WARP_DOUBLES * sizeof(double);
     if (!attr_set) {
@@ -443,7 +500,7 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     }
     // persistent-style grid: `ctas` CTAs of `warps` warps per SM; at least ~64 observations per warp
     const int64_t n_part_obs = p->N / n_parts + 1;
-    int64_t n_warps = std::min<int64_t>((n_part_obs + 63) / 64, (int64_t)p->sm_count * ctas * warps);
+    int64_t n_warps = std::min<int64_t>((n_part_obs + 64 * opl - 1) / (64 * opl), (int64_t)p->sm_count * ctas * warps);
     n_warps = std::max<int64_t>(1, std::min<int64_t>(n_warps, p->n_seg));
     PCS_TRY(ensure_ranges(p, n_warps, n_parts));
     const int grid = (int)((n_warps + warps - 1) / warps);

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "pcs_internal.cuh"
@@ -39,6 +40,13 @@ struct LmWorkspace {
     double* work = nullptr;
     int lwork = 0;
     int* info = nullptr;
+    // own dense SPD solve (k_chol_solve): diagonal-block factors, grid barrier counter
+    double* Ldiag = nullptr;   // [ceil(nc / 32)][32 * 32] row-major lower factors of the diagonal tiles
+    unsigned* bar = nullptr;
+    int chol_grid = 0;         // co-resident CTAs of k_chol_solve (0: use cuSOLVER)
+    // second set of normal-equation outputs: the trial point is evaluated speculatively with the full kernel
+    double* ne_alt = nullptr;
+    double* ne_orig = nullptr;
     // dense path
     double* H = nullptr;     // [n_free^2 + n_free + 1] = JtJ | Jtr | cost  (aliases p->dense)
     double* Hd = nullptr;    // damped copy [n_free^2]
@@ -333,9 +341,10 @@ void lm_free(pcs_problem* p)
     if (!w) return;
     if (w->blas) cublasDestroy(w->blas);
     if (w->solver) cusolverDnDestroy(w->solver);
-    double* ptrs[] = {w->L, w->y, w->Z, w->red, w->t, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs};
+    double* ptrs[] = {w->L, w->y, w->Z, w->red, w->t, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs, w->Ldiag, w->ne_alt};
     for (double* q : ptrs) if (q) cudaFree(q);
     if (w->info) cudaFree(w->info);
+    if (w->bar) cudaFree(w->bar);
     delete w;
     p->lm_ws = nullptr;
 }
@@ -365,6 +374,11 @@ static int lm_prepare(pcs_problem* p)
         w->red_doubles = w->nc * w->nc + 2 * w->nc + 1;
         PCS_CUDA(cudaMalloc((void**)&w->red, (size_t)w->red_doubles * 8));
         PCS_SOLVER(cusolverDnDpotrf_bufferSize(w->solver, CUBLAS_FILL_MODE_LOWER, (int)w->nc, w->red, (int)w->nc, &w->lwork));
+        // own persistent Cholesky solve (PCS_LM_CHOL=cusolver selects the library path for A/B runs)
+        const char* e = std::getenv("PCS_LM_CHOL");
+        if (!(e && e[0] == 'c')) PCS_TRY(chol_prepare(p->device, w->nc, &w->Ldiag, &w->bar, &w->chol_grid));
+        PCS_CUDA(cudaMalloc((void**)&w->ne_alt, (size_t)p->ne_doubles * 8));
+        w->ne_orig = p->ne;
     } else {
         const int64_t n = p->n_free;
         PCS_REQUIRE(n > 0 && n <= 32768, "dense LM path needs 0 < n_free <= 32768");
@@ -378,17 +392,27 @@ static int lm_prepare(pcs_problem* p)
     return PCS_OK;
 }
 
-// evaluate the normal equations at the current p->params (tables refreshed)
+// evaluate the normal equations at the current p->params (tables refreshed, reduction targets cleared in the same launch)
 static int eval_normal(pcs_problem* p)
 {
-    PCS_TRY(launch_prepare(p));
-    if (p->chain == PCS_CHAIN_TEMPLATE) return launch_normal_blocks(p);
-    return PCS_ERR_UNSUPPORTED;
+    if (p->chain != PCS_CHAIN_TEMPLATE) return PCS_ERR_UNSUPPORTED;
+    PCS_TRY(launch_prepare(p, false, nullptr, p->ne, (p->V - p->ne) + (int64_t)p->M * 42));
+    return launch_normal_blocks(p, true);
 }
 
-// One damped solve at the current linearisation.  On return w->delta holds the step (parameter-string layout)
-// and h_scal = {pred, |dx|^2, |x|^2, |g_pose|_inf, -, flag}.
-static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda, double* h_scal, double* h_ginf_cam, double* h_cost)
+// the two sets of normal-equation outputs [U | gc | cost | pad | V | gp | W] trade places
+static void swap_normal_buffers(pcs_problem* p, LmWorkspace* w)
+{
+    double* other = (p->ne == w->ne_orig) ? w->ne_alt : w->ne_orig;
+    const int64_t o_gc = p->gc - p->ne, o_cost = p->cost - p->ne, o_V = p->V - p->ne, o_gp = p->gp - p->ne, o_W = p->W - p->ne;
+    p->ne = other; p->U = other; p->gc = other + o_gc; p->cost = other + o_cost; p->V = other + o_V; p->gp = other + o_gp;
+    p->W = other + o_W;
+}
+
+// One damped solve at the current linearisation, enqueued without synchronising.  Afterwards w->delta holds the step
+// (parameter-string layout), w->scal = {pred, |dx|^2, |x|^2, |g_pose|_inf, |g_cam|_inf, flag, trial cost, -},
+// w->info the factorisation status and cost_r (inside w->red) the all-reduced r.r of the linearisation point.
+static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
 {
     cudaStream_t st = p->stream;
     const int64_t nc = w->nc, np = w->np;
@@ -413,8 +437,13 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda, double*
         if (rc != 0) { set_error("all-reduce callback failed"); return PCS_ERR_CUDA; }
     }
     k_lm_fix_diag<<<grid_for(nc, 256), 256, 0, st>>>(nc, Smat);
-    PCS_SOLVER(cusolverDnDpotrf(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, Smat, (int)nc, w->work, w->lwork, w->info));
-    PCS_SOLVER(cusolverDnDpotrs(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, 1, Smat, (int)nc, rhs, (int)nc, w->info));
+    if (w->chol_grid > 0) {
+        PCS_TRY(launch_chol_solve(st, w->chol_grid, nc, Smat, nc, rhs, w->Ldiag, w->bar, w->info));
+    } else {
+        PCS_SOLVER(cusolverDnDpotrf(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, Smat, (int)nc, w->work, w->lwork, w->info));
+        PCS_SOLVER(cusolverDnDpotrs(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, 1, Smat, (int)nc, rhs, (int)nc, w->info));
+    }
+    p->n_launches += 8;
     // rhs now holds delta_c
     PCS_BLAS(cublasDgemv(w->blas, CUBLAS_OP_T, (int)nc, (int)np, &one, w->Z, (int)nc, rhs, 1, &zero, w->t, 1));
     double* dp = w->delta + 15 * (int64_t)p->C;  // pose part of the parameter-string delta is written in place
@@ -430,15 +459,10 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda, double*
             return PCS_ERR_CUDA;
         }
     }
-    int h_info = 0;
-    PCS_CUDA(cudaMemcpyAsync(h_scal, w->scal, 8 * 8, cudaMemcpyDeviceToHost, st));
-    PCS_CUDA(cudaMemcpyAsync(&h_info, w->info, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PCS_CUDA(cudaMemcpyAsync(h_cost, cost_r, 8, cudaMemcpyDeviceToHost, st));
-    PCS_CUDA(cudaStreamSynchronize(st));
-    *h_ginf_cam = h_scal[4];
-    if (h_info != 0 || h_scal[5] != 0.0) return PCS_ERR_NUMERIC;
     return PCS_OK;
 }
+
+__global__ void k_copy_double(const double* __restrict__ src, double* __restrict__ dst) { *dst = *src; }
 
 }  // namespace pcs
 
@@ -495,9 +519,33 @@ int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in
     bool have_cost = false;
     while (rc == PCS_OK && it < o.max_iter) {
         ++it;
-        double ginf_cam = 0.0, cost_lin = 0.0;
+        double ginf_cam = 0.0, cost_lin = 0.0, cost_new = 0.0;
+        int h_info = 0;
         if (tmpl) {
-            rc = solve_template(p, w, lambda, h_scal, &ginf_cam, &cost_lin);
+            // Template chain: the damped solve, the step and the evaluation of the TRIAL point with the full
+            // normal-equation kernel (into the second output set) are enqueued back to back and read with ONE
+            // synchronisation per iteration.  An accepted step already has its linearisation; a rejected one only
+            // costs the difference between the full kernel and a residual-only pass.
+            rc = solve_template(p, w, lambda);
+            if (rc != PCS_OK) break;
+            PCS_CUDA(cudaMemcpyAsync(w->backup, p->params, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
+            k_axpy_params<<<grid_for(p->L, 256), 256, 0, st>>>(p->L, w->delta, p->params);
+            swap_normal_buffers(p, w);
+            rc = eval_lin();
+            if (rc != PCS_OK) break;
+            k_copy_double<<<1, 1, 0, st>>>(p->cost, w->scal + 6);
+            if (p->allreduce && p->allreduce(p->allreduce_user, w->scal + 6, 1, 0, (void*)st) != 0) {
+                set_error("all-reduce callback failed");
+                rc = PCS_ERR_CUDA;
+                break;
+            }
+            PCS_CUDA(cudaMemcpyAsync(h_scal, w->scal, 8 * 8, cudaMemcpyDeviceToHost, st));
+            PCS_CUDA(cudaMemcpyAsync(&h_info, w->info, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PCS_CUDA(cudaMemcpyAsync(&cost_lin, w->red + w->nc * w->nc + 2 * w->nc, 8, cudaMemcpyDeviceToHost, st));
+            PCS_CUDA(cudaStreamSynchronize(st));
+            ginf_cam = h_scal[4];
+            cost_new = h_scal[6];
+            if (h_info != 0 || h_scal[5] != 0.0) rc = PCS_ERR_NUMERIC;
         } else {
             double *H = w->H, *g = w->H + n * n, *c = g + n;
             PCS_CUDA(cudaMemsetAsync(w->scal, 0, 8 * 8, st));
@@ -505,15 +553,23 @@ int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in
             PCS_SOLVER(cusolverDnDpotrf(w->solver, CUBLAS_FILL_MODE_LOWER, (int)n, w->Hd, (int)n, w->work, w->lwork, w->info));
             PCS_SOLVER(cusolverDnDpotrs(w->solver, CUBLAS_FILL_MODE_LOWER, (int)n, 1, w->Hd, (int)n, w->rhs, (int)n, w->info));
             k_dense_delta<<<grid_for(n, 128), 128, 0, st>>>(n, lambda, w->rhs, H, g, p->free_idx, p->params, w->delta, w->scal);
-            int h_info = 0;
             PCS_CUDA(cudaMemcpyAsync(h_scal, w->scal, 8 * 8, cudaMemcpyDeviceToHost, st));
             PCS_CUDA(cudaMemcpyAsync(&h_info, w->info, sizeof(int), cudaMemcpyDeviceToHost, st));
             PCS_CUDA(cudaMemcpyAsync(&cost_lin, c, 8, cudaMemcpyDeviceToHost, st));
             PCS_CUDA(cudaStreamSynchronize(st));
             if (h_info != 0) rc = PCS_ERR_NUMERIC;
         }
+        // the template chain has already moved to the trial point: undo = old parameters + old output set
+        auto undo_trial = [&]() -> int {
+            if (!tmpl) return PCS_OK;
+            PCS_CUDA(cudaMemcpyAsync(p->params, w->backup, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
+            swap_normal_buffers(p, w);
+            --n_normal;   // the speculative evaluation is not a linearisation that was used
+            ++n_cost;
+            return PCS_OK;
+        };
         if (rc == PCS_ERR_NUMERIC) {  // not positive definite at this damping: raise lambda and retry
-            rc = PCS_OK;
+            rc = undo_trial();
             lambda = std::min(lambda * 10.0, o.lambda_max);
             if (lambda >= o.lambda_max) { status = -1; break; }
             continue;
@@ -521,23 +577,24 @@ int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in
         if (rc != PCS_OK) break;
         if (!have_cost) { cost = cost0 = cost_lin; have_cost = true; }
         ginf = std::max(ginf_cam, h_scal[3]);
-        if (ginf < o.gtol) { status = 1; break; }
+        if (ginf < o.gtol) { status = 1; rc = undo_trial(); break; }
         const double pred = h_scal[0], dx = std::sqrt(h_scal[1]), xn = std::sqrt(h_scal[2]);
-        if (dx < o.xtol * (o.xtol + xn)) { status = 3; break; }
-        // trial point
-        PCS_CUDA(cudaMemcpyAsync(w->backup, p->params, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
-        k_axpy_params<<<grid_for(p->L, 256), 256, 0, st>>>(p->L, w->delta, p->params);
-        PCS_TRY(launch_prepare(p));
-        PCS_TRY(launch_cost_only(p, w->scal + 6));
-        double cost_new = 0.0;
-        ++n_cost;
-        if (p->allreduce && p->allreduce(p->allreduce_user, w->scal + 6, 1, 0, (void*)st) != 0) {
-            set_error("all-reduce callback failed");
-            rc = PCS_ERR_CUDA;
-            break;
+        if (dx < o.xtol * (o.xtol + xn)) { status = 3; rc = undo_trial(); break; }
+        if (!tmpl) {
+            // trial point, residual-only pass
+            PCS_CUDA(cudaMemcpyAsync(w->backup, p->params, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
+            k_axpy_params<<<grid_for(p->L, 256), 256, 0, st>>>(p->L, w->delta, p->params);
+            PCS_TRY(launch_prepare(p));
+            PCS_TRY(launch_cost_only(p, w->scal + 6));
+            ++n_cost;
+            if (p->allreduce && p->allreduce(p->allreduce_user, w->scal + 6, 1, 0, (void*)st) != 0) {
+                set_error("all-reduce callback failed");
+                rc = PCS_ERR_CUDA;
+                break;
+            }
+            PCS_CUDA(cudaMemcpyAsync(&cost_new, w->scal + 6, 8, cudaMemcpyDeviceToHost, st));
+            PCS_CUDA(cudaStreamSynchronize(st));
         }
-        PCS_CUDA(cudaMemcpyAsync(&cost_new, w->scal + 6, 8, cudaMemcpyDeviceToHost, st));
-        PCS_CUDA(cudaStreamSynchronize(st));
         const double actual = cost - cost_new;          // in units of r.r
         const double rho = (pred > 0.0 && std::isfinite(cost_new)) ? actual / pred : -1.0;
         if (o.verbose)
@@ -549,15 +606,22 @@ int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in
             const double f = 1.0 - std::pow(2.0 * rho - 1.0, 3.0);
             lambda = std::max(o.lambda_min, lambda * std::max(1.0 / 3.0, f));
             nu = 2.0;
-            rc = eval_lin();
-            if (rc != PCS_OK) break;
+            if (!tmpl) {
+                rc = eval_lin();
+                if (rc != PCS_OK) break;
+            }
             if (rel < o.ftol) { status = 2; break; }
         } else {
-            PCS_CUDA(cudaMemcpyAsync(p->params, w->backup, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
+            if (tmpl) rc = undo_trial();
+            else PCS_CUDA(cudaMemcpyAsync(p->params, w->backup, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
             lambda = std::min(o.lambda_max, lambda * nu);
             nu *= 2.0;
             if (lambda >= o.lambda_max) { status = -1; break; }
         }
+    }
+    if (tmpl && p->ne != w->ne_orig) {   // callers hold pointers into the original output set (pcs_device_pointers)
+        PCS_CUDA(cudaMemcpyAsync(w->ne_orig, p->ne, (size_t)p->ne_doubles * 8, cudaMemcpyDeviceToDevice, st));
+        swap_normal_buffers(p, w);
     }
     if (rc == PCS_OK) {
         PCS_TRY(launch_prepare(p));
