@@ -202,6 +202,12 @@ PCS_API int pcs_lm_solve(pcs_problem* p, const double* x0 /*[n_free]*/, const pc
  * Exposed so that the solver kernel can be tested on its own. */
 PCS_API int pcs_spd_solve(int device, int64_t n, const double* A, const double* b, double* x /*[n]*/, int* info);
 
+/* S -= Z Z^T on the lower triangle, the pose-elimination update of the reduced camera system as pcs_lm_solve runs it
+ * (stream-K tiled FP64 tensor-path kernel, csrc/pcs_schur.cu).  Host buffers; Z is column-major [k][n] (n rows
+ * contiguous), S column-major [n][n], only its lower triangle is updated.  Exposed so that the kernel can be tested
+ * on its own. */
+PCS_API int pcs_syrk_sub(int device, int64_t n, int64_t k, const double* Z, double* S);
+
 /* Optional kernel timing: when enabled, every launch of the fused normal-equation kernel is bracketed by a pair of
  * CUDA events on the problem's stream (a ring of 1024 pairs, so a timed loop needs no synchronisation inside).
  * pcs_timing_get returns the duration (ms) of the most recent launch, pcs_timing_get_all the durations of the last

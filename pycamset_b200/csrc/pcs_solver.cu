@@ -430,7 +430,9 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
                                                                         Smat, rhs, gcopy, cost_r, p->rank == 0);
     PCS_CUDA(cudaGetLastError());
     const double minus1 = -1.0, one = 1.0, zero = 0.0;
-    PCS_BLAS(cublasDsyrk(w->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, &one, Smat, (int)nc));
+    static const bool lib_syrk = [] { const char* e = std::getenv("PCS_LM_SYRK"); return e && e[0] == 'c'; }();   // A/B runs
+    if (lib_syrk) PCS_BLAS(cublasDsyrk(w->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, &one, Smat, (int)nc));
+    else PCS_TRY(launch_schur_syrk(st, p->sm_count, nc, np, w->Z, Smat));
     PCS_BLAS(cublasDgemv(w->blas, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, w->y, 1, &one, rhs, 1));
     if (p->allreduce) {
         int rc = p->allreduce(p->allreduce_user, w->red, w->red_doubles, 0, (void*)st);
