@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--cpu-sample-obs", type=int, default=1_000_000)
     ap.add_argument("--no-lm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-callbacks", action="store_true", help="skip the K_res / K_jac (loss_fun / jac_fn drop-in) rates")
     ap.add_argument("--lm-iters", type=int, default=10)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: camera-block all-reduce path")
     args = ap.parse_args()
@@ -418,6 +419,38 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = n_total / (float(e2e_t.item()) / e2e_steps) / 1e6
 
+    # ---- the reference's own callbacks (loss_fun / jac_fn drop-ins): HBM-bound kernels, reported beside the headline --
+    # K_res: 28 B in + 16 B out per observation; K_jac: 28 B in + 8 B per stored CSR value.  N = 1 only (rank-local
+    # kernels, no exchange); inputs resident, L2 flushed between calls, CUDA events on the problem's stream.
+    callbacks = None
+    if world == 1 and not args.no_callbacks:
+        try:
+            peak_hbm, _ = peaks()
+            nnz = prob.nnz
+            r_dev = torch.empty(2 * n_local, dtype=torch.float64, device=f"cuda:{dev}")
+            v_dev = torch.empty(max(nnz, 1), dtype=torch.float64, device=f"cuda:{dev}")
+            callbacks = {}
+            with torch.cuda.stream(stream):
+                for name, fn, nbytes in (
+                        ("K_res", lambda: prob.residual_device(r_dev.data_ptr(), x_dev.data_ptr()), 44.0 * n_local),
+                        ("K_jac", lambda: prob.jacobian_values_device(v_dev.data_ptr(), x_dev.data_ptr()), 28.0 * n_local + 8.0 * nnz)):
+                    for _ in range(3):
+                        fn()
+                    ts = []
+                    for _ in range(20):
+                        flush_buf.zero_()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(stream); fn(); e1.record(stream)
+                        torch.cuda.synchronize(dev)
+                        ts.append(e0.elapsed_time(e1))
+                    ms = float(np.median(ts))
+                    callbacks[name] = {"ms_per_call": ms, "Mobs_per_s": n_local / ms / 1e3, "algorithmic_GBps": nbytes / ms / 1e6,
+                                       "frac_of_hbm_peak": nbytes / ms / 1e6 / peak_hbm,
+                                       "includes": "table set-up launch + kernel"}
+            del r_dev, v_dev
+        except Exception as e:  # report, never hide
+            callbacks = {"error": str(e)[:200]}
+
     # ---- LM iterations / s (device-resident solve; all-reduce of the reduced camera system for N > 1) --------------
     lm = None
     if not args.no_lm:
@@ -474,7 +507,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mobs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "call": "BundleProblem.normal_equations(x_host) -> U, gc, V, gp, W, cost on host"},
-            "gpu_launches": gpu_launches, "clocks": clocks, "lm": lm,
+            "gpu_launches": gpu_launches, "clocks": clocks, "lm": lm, "callbacks": callbacks,
             "setup_s": setup_s, "wall_s_timed_region": wall_s,
         }
         print(json.dumps(out), flush=True)
