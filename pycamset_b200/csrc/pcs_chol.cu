@@ -34,7 +34,8 @@ struct CholProblem {
     double* A;        // [n][ld] column-major, lower triangle
     double* rhs;      // [n]
     double* Ldiag;    // [nb][32 * 32] row-major
-    unsigned* bar;
+    unsigned long long* bar;   // monotonic arrival counter, never reset: the launch passes the value it starts from
+    unsigned long long bar_base;
     int* info;
     int64_t n, ld;
     int nb;
@@ -261,16 +262,16 @@ __device__ __forceinline__ void tile_trsm(double* __restrict__ T, const double* 
     for (int c = 0; c < TB; ++c) T[c * TP + lane] = x[c];
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* info)
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int* info)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v;
+        atomicAdd(bar, 1ull);
+        unsigned long long v;
         int spins = 0;
         do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
         } while (v < target && ++spins < (1 << 24));
         if (v < target) *info = -2;   // a CTA never arrived: give up instead of hanging the device
     }
@@ -374,7 +375,7 @@ k_chol_solve(CholProblem P)
             __syncthreads();
         }
         trace_stamp(P, k, 3);
-        grid_barrier(P.bar, (unsigned)(k + 1) * gridDim.x, P.info);
+        grid_barrier(P.bar, P.bar_base + (unsigned long long)(k + 1) * gridDim.x, P.info);
         trace_stamp(P, k, 4);
     }
     if (blockIdx.x != 0) return;
@@ -478,7 +479,7 @@ size_t chol_smem_bytes(int nb)
 }  // namespace
 
 // Workspace + launch geometry.  grid = 0 on return means "not usable here" (caller falls back to cuSOLVER).
-int chol_prepare(int device, int64_t n, double** Ldiag, unsigned** bar, int* grid)
+int chol_prepare(int device, int64_t n, double** Ldiag, unsigned long long** bar, int* grid)
 {
     *grid = 0;
     const int nb = (int)((n + TB - 1) / TB);
@@ -494,20 +495,23 @@ int chol_prepare(int device, int64_t n, double** Ldiag, unsigned** bar, int* gri
     if (per_sm < 1) return PCS_OK;
     const int n_tiles0 = nb + nb * (nb + 1) / 2;   // upper bound of the tiles of a phase
     PCS_CUDA(cudaMalloc((void**)Ldiag, (size_t)nb * TB * TB * sizeof(double)));
-    PCS_CUDA(cudaMalloc((void**)bar, sizeof(unsigned)));
+    PCS_CUDA(cudaMalloc((void**)bar, sizeof(unsigned long long)));
+    PCS_CUDA(cudaMemset(*bar, 0, sizeof(unsigned long long)));
     *grid = std::max(1, std::min(sms, n_tiles0));
     return PCS_OK;
 }
 
-int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t ld, double* rhs, double* Ldiag, unsigned* bar,
-                      int* info, long long* trace)
+// *bar_base: the caller's running count of barrier arrivals on `bar` (starts at 0 with a zeroed counter); advanced here.
+// `info` must be zero on entry (the kernel only ever raises it).
+int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t ld, double* rhs, double* Ldiag,
+                      unsigned long long* bar, unsigned long long* bar_base, int* info, long long* trace)
 {
     CholProblem P;
     P.trace = trace;
     P.A = A; P.rhs = rhs; P.Ldiag = Ldiag; P.bar = bar; P.info = info; P.n = n; P.ld = ld;
     P.nb = (int)((n + TB - 1) / TB);
-    PCS_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
-    PCS_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    P.bar_base = *bar_base;
+    *bar_base += (unsigned long long)P.nb * (unsigned long long)grid;
     void* args[] = {&P};
     PCS_CUDA(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_THREADS), args, chol_smem_bytes(P.nb), st));
     return PCS_OK;
@@ -521,7 +525,8 @@ extern "C" int pcs_spd_solve(int device, int64_t n, const double* A, const doubl
     PCS_REQUIRE(n > 0 && A && b && x, "NULL argument or n <= 0");
     PCS_CUDA(cudaSetDevice(device));
     double *dA = nullptr, *db = nullptr, *Ldiag = nullptr;
-    unsigned* bar = nullptr;
+    unsigned long long* bar = nullptr;
+    unsigned long long bar_base = 0;
     int* dinfo = nullptr;
     int grid = 0;
     int rc = chol_prepare(device, n, &Ldiag, &bar, &grid);
@@ -533,8 +538,9 @@ extern "C" int pcs_spd_solve(int device, int64_t n, const double* A, const doubl
     if (e == cudaSuccess) e = cudaMalloc((void**)&dinfo, sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(dA, A, (size_t)(n * n) * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(db, b, (size_t)n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(dinfo, 0, sizeof(int));
     if (e != cudaSuccess) { set_error(std::string("pcs_spd_solve: ") + cudaGetErrorString(e)); cleanup(); return PCS_ERR_CUDA; }
-    rc = launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, dinfo);
+    rc = launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, &bar_base, dinfo, nullptr);
     int h_info = 0;
     if (rc == PCS_OK) {
         e = cudaDeviceSynchronize();

@@ -119,8 +119,8 @@ void lm_free(pcs_problem* p);
 // pcs_schur.cu: S (n x n, column-major, lower) -= Z Z^T, Z column-major [k][n]
 int launch_schur_syrk(cudaStream_t st, int sm_count, int64_t n, int64_t k, const double* Z, double* S);
 // pcs_chol.cu: dense SPD solve of the reduced camera system in one persistent kernel
-int chol_prepare(int device, int64_t n, double** Ldiag, unsigned** bar, int* grid);
-int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t ld, double* rhs, double* Ldiag, unsigned* bar,
-                      int* info, long long* trace = nullptr);
+int chol_prepare(int device, int64_t n, double** Ldiag, unsigned long long** bar, int* grid);
+int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t ld, double* rhs, double* Ldiag,
+                      unsigned long long* bar, unsigned long long* bar_base, int* info, long long* trace = nullptr);
 void p2p_free(pcs_problem* p);
 }  // namespace pcs

@@ -42,11 +42,15 @@ struct LmWorkspace {
     int* info = nullptr;
     // own dense SPD solve (k_chol_solve): diagonal-block factors, grid barrier counter
     double* Ldiag = nullptr;   // [ceil(nc / 32)][32 * 32] row-major lower factors of the diagonal tiles
-    unsigned* bar = nullptr;
+    unsigned long long* bar = nullptr;
+    unsigned long long bar_base = 0;
     int chol_grid = 0;         // co-resident CTAs of k_chol_solve (0: use cuSOLVER)
     // second set of normal-equation outputs: the trial point is evaluated speculatively with the full kernel
     double* ne_alt = nullptr;
     double* ne_orig = nullptr;
+    // one pinned read-back per iteration: scal[8] | info | cost of the linearisation point (gathered on the device)
+    double* h_read = nullptr;   // pinned [10]
+    double* d_read = nullptr;   // [10]
     // dense path
     double* H = nullptr;     // [n_free^2 + n_free + 1] = JtJ | Jtr | cost  (aliases p->dense)
     double* Hd = nullptr;    // damped copy [n_free^2]
@@ -155,25 +159,32 @@ __global__ void k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict_
     for (int i = 0; i < 6; ++i) Z[((int64_t)m * 6 + i) * nc + (int64_t)c * 15 + a] = z[i];
 }
 
-// S = blockdiag(U masked + lambda D), rhs = -gc masked, gc copy (for the convergence test)
+// S = blockdiag(U masked + lambda D) with every other entry zero (each entry of S is written exactly once: no memset),
+// rhs = -gc masked, gc copy (for the convergence test); also clears the step scalars and the factorisation status.
 __global__ void k_lm_init_reduced(int C, int64_t nc, double lambda, const double* __restrict__ U, const double* __restrict__ gc,
                                   const double* __restrict__ cost, const uint16_t* __restrict__ cam_mask, double* __restrict__ Smat,
-                                  double* __restrict__ rhs, double* __restrict__ gcopy, double* __restrict__ cost_out, int rank0)
+                                  double* __restrict__ rhs, double* __restrict__ gcopy, double* __restrict__ cost_out,
+                                  double* __restrict__ scal, int* __restrict__ info)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= C * 225) return;
-    const int c = t / 225, e = t % 225, a = e / 15, b = e % 15;
-    const unsigned mask = cam_mask[c];
-    const bool fa = mask & (1u << a), fb = mask & (1u << b);
-    double v = (fa && fb) ? U[t] : 0.0;
-    if (a == b) {
-        // fixed rows: zero here, set to the identity after the all-reduce (k_lm_fix_diag)
-        v = fa ? v + lambda * v : 0.0;
-        rhs[(int64_t)c * 15 + a] = fa ? -gc[c * 15 + a] : 0.0;
-        gcopy[(int64_t)c * 15 + a] = fa ? gc[c * 15 + a] : 0.0;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < 8) scal[t] = 0.0;
+    if (t == 8) { *info = 0; *cost_out = *cost; }
+    if (t >= nc * nc) return;
+    const int64_t col = t / nc, row = t % nc;      // column-major S
+    const int c = (int)(row / 15), a = (int)(row % 15), cb = (int)(col / 15), b = (int)(col % 15);
+    double v = 0.0;
+    if (c == cb) {
+        const unsigned mask = cam_mask[c];
+        const bool fa = mask & (1u << a), fb = mask & (1u << b);
+        v = (fa && fb) ? U[(int64_t)c * 225 + a * 15 + b] : 0.0;
+        if (a == b) {
+            // fixed rows: zero here, set to the identity after the all-reduce (k_lm_fix_diag)
+            v = fa ? v + lambda * v : 0.0;
+            rhs[row] = fa ? -gc[row] : 0.0;
+            gcopy[row] = fa ? gc[row] : 0.0;
+        }
     }
-    Smat[((int64_t)c * 15 + b) * nc + (int64_t)c * 15 + a] = v;
-    if (t == 0) *cost_out = *cost;
+    Smat[t] = v;
 }
 
 // rows whose diagonal is exactly zero after the reduction (fixed, or unobserved by every rank) -> identity
@@ -274,6 +285,32 @@ __global__ void k_axpy_params(int64_t n, const double* __restrict__ delta, doubl
     if (i < n) params[i] += delta[i];
 }
 
+// backup <- params, params += delta (the move to the trial point), and scal[4] = |g_cam|_inf in the same launch
+__global__ void k_lm_take_step(int64_t L, int64_t nc, const double* __restrict__ delta, double* __restrict__ params,
+                               double* __restrict__ backup, const double* __restrict__ gcopy, double* __restrict__ scal)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < L) {
+        const double v = params[i];
+        backup[i] = v;
+        params[i] = v + delta[i];
+    }
+    double m = i < nc ? fabs(gcopy[i]) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax((unsigned long long*)(scal + 4), (unsigned long long)__double_as_longlong(m));
+}
+
+// everything the host reads after an iteration, gathered into one buffer: scal[0..7] | info | cost of the linearisation
+__global__ void k_lm_gather_readback(const double* __restrict__ scal, const int* __restrict__ info, const double* __restrict__ cost_lin,
+                                     const double* __restrict__ cost_trial, double* __restrict__ out)
+{
+    const int t = threadIdx.x;
+    if (t < 8) out[t] = (t == 6 && cost_trial) ? *cost_trial : scal[t];
+    if (t == 8) out[8] = (double)*info;
+    if (t == 9) out[9] = *cost_lin;
+}
+
 __global__ void k_max_abs(int64_t n, const double* __restrict__ v, double* __restrict__ out)
 {
     double m = 0.0;
@@ -345,6 +382,8 @@ void lm_free(pcs_problem* p)
     for (double* q : ptrs) if (q) cudaFree(q);
     if (w->info) cudaFree(w->info);
     if (w->bar) cudaFree(w->bar);
+    if (w->h_read) cudaFreeHost(w->h_read);
+    if (w->d_read) cudaFree(w->d_read);
     delete w;
     p->lm_ws = nullptr;
 }
@@ -362,6 +401,8 @@ static int lm_prepare(pcs_problem* p)
     PCS_CUDA(cudaMalloc((void**)&w->backup, (size_t)p->L * 8));
     PCS_CUDA(cudaMalloc((void**)&w->scal, 8 * 8));
     PCS_CUDA(cudaMalloc((void**)&w->info, sizeof(int)));
+    PCS_CUDA(cudaMalloc((void**)&w->d_read, 10 * 8));
+    PCS_CUDA(cudaMallocHost((void**)&w->h_read, 10 * 8));
     PCS_CUDA(cudaMemsetAsync(w->delta, 0, (size_t)p->L * 8, p->stream));
     if (p->chain == PCS_CHAIN_TEMPLATE) {
         w->nc = 15 * (int64_t)p->C;
@@ -420,14 +461,12 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     double* rhs = w->red + nc * nc;
     double* gcopy = rhs + nc;
     double* cost_r = gcopy + nc;
-    PCS_CUDA(cudaMemsetAsync(w->scal, 0, 8 * 8, st));
-    PCS_CUDA(cudaMemsetAsync(Smat, 0, (size_t)(nc * nc) * 8, st));
+    k_lm_init_reduced<<<grid_for(std::max<int64_t>(nc * nc, 9), 256), 256, 0, st>>>(p->C, nc, lambda, p->U, p->gc, p->cost, p->cam_mask,
+                                                                                  Smat, rhs, gcopy, cost_r, w->scal, w->info);
     k_lm_pose_factor<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, lambda, p->V, p->gp, p->pose_mask, w->L, w->y, w->scal);
     if (p->n_seg)
         k_lm_segment_Z<<<grid_for(p->n_seg * 15, 256), 256, 0, st>>>(p->n_seg, nc, p->seg_cam, p->seg_pose, p->W, w->L,
                                                                      p->cam_mask, p->pose_mask, w->Z);
-    k_lm_init_reduced<<<grid_for((int64_t)p->C * 225, 256), 256, 0, st>>>(p->C, nc, lambda, p->U, p->gc, p->cost, p->cam_mask,
-                                                                        Smat, rhs, gcopy, cost_r, p->rank == 0);
     PCS_CUDA(cudaGetLastError());
     const double minus1 = -1.0, one = 1.0, zero = 0.0;
     static const bool lib_syrk = [] { const char* e = std::getenv("PCS_LM_SYRK"); return e && e[0] == 'c'; }();   // A/B runs
@@ -440,7 +479,7 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     }
     k_lm_fix_diag<<<grid_for(nc, 256), 256, 0, st>>>(nc, Smat);
     if (w->chol_grid > 0) {
-        PCS_TRY(launch_chol_solve(st, w->chol_grid, nc, Smat, nc, rhs, w->Ldiag, w->bar, w->info));
+        PCS_TRY(launch_chol_solve(st, w->chol_grid, nc, Smat, nc, rhs, w->Ldiag, w->bar, &w->bar_base, w->info));
     } else {
         PCS_SOLVER(cusolverDnDpotrf(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, Smat, (int)nc, w->work, w->lwork, w->info));
         PCS_SOLVER(cusolverDnDpotrs(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, 1, Smat, (int)nc, rhs, (int)nc, w->info));
@@ -452,7 +491,6 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     k_lm_pose_back<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, w->L, w->y, w->t, dp);
     k_lm_assemble_delta<<<grid_for(15 * (int64_t)p->C + 6 * (int64_t)p->M, 128), 128, 0, st>>>(
         p->C, p->M, lambda, rhs, dp, p->U, p->gc, p->V, p->gp, p->cam_mask, p->pose_mask, p->params, w->delta, w->scal, p->rank == 0);
-    k_max_abs<<<std::max(1, std::min(64, grid_for(nc, 256))), 256, 0, st>>>(nc, gcopy, w->scal + 4);
     PCS_CUDA(cudaGetLastError());
     if (p->allreduce) {  // pred, |dx|^2, |x|^2 are partial sums over this rank's poses; the pose gradient norm is a max
         if (p->allreduce(p->allreduce_user, w->scal, 3, 0, (void*)st) != 0 ||
@@ -530,21 +568,28 @@ int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in
             // costs the difference between the full kernel and a residual-only pass.
             rc = solve_template(p, w, lambda);
             if (rc != PCS_OK) break;
-            PCS_CUDA(cudaMemcpyAsync(w->backup, p->params, (size_t)p->L * 8, cudaMemcpyDeviceToDevice, st));
-            k_axpy_params<<<grid_for(p->L, 256), 256, 0, st>>>(p->L, w->delta, p->params);
+            double* gcopy = w->red + w->nc * w->nc + w->nc;
+            k_lm_take_step<<<grid_for(std::max<int64_t>(p->L, w->nc), 256), 256, 0, st>>>(p->L, w->nc, w->delta, p->params, w->backup,
+                                                                                       gcopy, w->scal);
             swap_normal_buffers(p, w);
             rc = eval_lin();
             if (rc != PCS_OK) break;
-            k_copy_double<<<1, 1, 0, st>>>(p->cost, w->scal + 6);
-            if (p->allreduce && p->allreduce(p->allreduce_user, w->scal + 6, 1, 0, (void*)st) != 0) {
-                set_error("all-reduce callback failed");
-                rc = PCS_ERR_CUDA;
-                break;
+            const double* trial_cost = p->cost;
+            if (p->allreduce) {   // the trial cost is a partial sum: combine a copy (p->cost itself feeds the next reduction)
+                k_copy_double<<<1, 1, 0, st>>>(p->cost, w->scal + 6);
+                if (p->allreduce(p->allreduce_user, w->scal + 6, 1, 0, (void*)st) != 0) {
+                    set_error("all-reduce callback failed");
+                    rc = PCS_ERR_CUDA;
+                    break;
+                }
+                trial_cost = nullptr;
             }
-            PCS_CUDA(cudaMemcpyAsync(h_scal, w->scal, 8 * 8, cudaMemcpyDeviceToHost, st));
-            PCS_CUDA(cudaMemcpyAsync(&h_info, w->info, sizeof(int), cudaMemcpyDeviceToHost, st));
-            PCS_CUDA(cudaMemcpyAsync(&cost_lin, w->red + w->nc * w->nc + 2 * w->nc, 8, cudaMemcpyDeviceToHost, st));
+            k_lm_gather_readback<<<1, 32, 0, st>>>(w->scal, w->info, gcopy + w->nc, trial_cost, w->d_read);
+            PCS_CUDA(cudaMemcpyAsync(w->h_read, w->d_read, 10 * 8, cudaMemcpyDeviceToHost, st));
             PCS_CUDA(cudaStreamSynchronize(st));
+            std::memcpy(h_scal, w->h_read, 8 * 8);
+            h_info = (int)w->h_read[8];
+            cost_lin = w->h_read[9];
             ginf_cam = h_scal[4];
             cost_new = h_scal[6];
             if (h_info != 0 || h_scal[5] != 0.0) rc = PCS_ERR_NUMERIC;

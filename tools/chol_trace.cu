@@ -13,20 +13,20 @@ int main(int argc, char** argv)
     std::normal_distribution<double> nd;
     for (int64_t i = 0; i < n; ++i) for (int64_t j = 0; j <= i; ++j) { double v = 0.01 * nd(g); A[j * n + i] = v; A[i * n + j] = v; }
     for (int64_t i = 0; i < n; ++i) A[i * n + i] = n * 0.02 + 1.0;
-    double *dA, *db, *Ldiag; unsigned* bar; int* info; long long* tr; int grid;
+    double *dA, *db, *Ldiag; unsigned long long* bar; unsigned long long bar_base = 0; int* info; long long* tr; int grid;
     const int nb = (int)((n + 31) / 32);
     chol_prepare(0, n, &Ldiag, &bar, &grid);
-    cudaMalloc(&dA, n * n * 8); cudaMalloc(&db, n * 8); cudaMalloc(&info, 4); cudaMalloc(&tr, (nb + 1) * 8 * 8);
+    cudaMalloc(&dA, n * n * 8); cudaMalloc(&db, n * 8); cudaMalloc(&info, 4); cudaMemset(info, 0, 4); cudaMalloc(&tr, (nb + 1) * 8 * 8);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms = 0;
     // warm the clocks up: ~0.5 s of back-to-back solves before the traced one
-    for (int rep = 0; rep < 2000; ++rep) launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, info, nullptr);
+    for (int rep = 0; rep < 2000; ++rep) launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, &bar_base, info, nullptr);
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int rep = 0; rep < 20; ++rep) {
         cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice); cudaMemcpy(db, b.data(), n * 8, cudaMemcpyHostToDevice);
         cudaEventRecord(e0);
-        launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, info, nullptr);
+        launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, &bar_base, info, nullptr);
         cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
@@ -34,7 +34,7 @@ int main(int argc, char** argv)
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice); cudaMemcpy(db, b.data(), n * 8, cudaMemcpyHostToDevice);
         cudaEventRecord(e0);
-        launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, info, tr);
+        launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, &bar_base, info, tr);
         cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     }
     std::vector<long long> h((nb + 1) * 8);
