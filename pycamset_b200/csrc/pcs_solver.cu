@@ -134,29 +134,53 @@ __global__ void k_lm_pose_factor(int M, double lambda, const double* __restrict_
     }
 }
 
-// Z rows of one segment: z = w L^-T  (solve L z^T = w^T), scattered into the dense column-major Z
-__global__ void k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose,
-                               const double* __restrict__ W, const double* __restrict__ L, const uint16_t* __restrict__ cam_mask,
-                               const uint8_t* __restrict__ pose_mask, double* __restrict__ Z)
+// Z rows of one segment: z = w L^-T  (solve L z^T = w^T), scattered into the dense column-major Z.  The same threads
+// also form the pose part of the reduced right-hand side, rhs_c -= Z_{c,m} y_m: segments are sorted by camera, so a
+// block's contributions fall on at most a few cameras and are combined in shared memory before they reach global
+// memory (one FP64 reduction per block, camera and row instead of one per segment and row).
+constexpr int Z_CAM_WIN = 4;
+__global__ void __launch_bounds__(256)
+k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose,
+               const double* __restrict__ W, const double* __restrict__ L, const double* __restrict__ y,
+               const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask, double* __restrict__ Z,
+               double* __restrict__ rhs)
 {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= S * 15) return;
-    const int64_t s = t / 15;
-    const int a = (int)(t % 15);
-    const int c = seg_cam[s], m = seg_pose[s];
-    const bool row_free = cam_mask[c] & (1u << a);
-    const unsigned pm = pose_mask[m];
-    const double* Lm = L + (int64_t)m * 36;
-    double z[6];
+    __shared__ double s_acc[Z_CAM_WIN * 15];
+    __shared__ int s_c0;
+    const int64_t t0 = blockIdx.x * (int64_t)blockDim.x;
+    if (threadIdx.x < Z_CAM_WIN * 15) s_acc[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) s_c0 = seg_cam[min(t0 / 15, S - 1)];
+    __syncthreads();
+    const int64_t t = t0 + threadIdx.x;
+    if (t < S * 15) {
+        const int64_t s = t / 15;
+        const int a = (int)(t % 15);
+        const int c = seg_cam[s], m = seg_pose[s];
+        const bool row_free = cam_mask[c] & (1u << a);
+        const unsigned pm = pose_mask[m];
+        const double* Lm = L + (int64_t)m * 36;
+        double z[6], dot = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        double w = (row_free && (pm & (1u << i))) ? W[s * 90 + a * 6 + i] : 0.0;
+        for (int i = 0; i < 6; ++i) {
+            double w = (row_free && (pm & (1u << i))) ? W[s * 90 + a * 6 + i] : 0.0;
 #pragma unroll
-        for (int k = 0; k < i; ++k) w -= Lm[i * 6 + k] * z[k];
-        z[i] = w / Lm[i * 6 + i];
+            for (int k = 0; k < i; ++k) w -= Lm[i * 6 + k] * z[k];
+            z[i] = w / Lm[i * 6 + i];
+            dot = fma(z[i], y[(int64_t)m * 6 + i], dot);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Z[((int64_t)m * 6 + i) * nc + (int64_t)c * 15 + a] = z[i];
+        const int cw = c - s_c0;
+        if (dot != 0.0) {
+            if (cw >= 0 && cw < Z_CAM_WIN) atomicAdd(&s_acc[cw * 15 + a], -dot);
+            else atomicAdd(rhs + (int64_t)c * 15 + a, -dot);
+        }
     }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) Z[((int64_t)m * 6 + i) * nc + (int64_t)c * 15 + a] = z[i];
+    __syncthreads();
+    if (threadIdx.x < Z_CAM_WIN * 15) {
+        const double v = s_acc[threadIdx.x];
+        if (v != 0.0) atomicAdd(rhs + (int64_t)(s_c0 + threadIdx.x / 15) * 15 + threadIdx.x % 15, v);
+    }
 }
 
 // S = blockdiag(U masked + lambda D) with every other entry zero (each entry of S is written exactly once: no memset),
@@ -465,14 +489,13 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
                                                                                   Smat, rhs, gcopy, cost_r, w->scal, w->info);
     k_lm_pose_factor<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, lambda, p->V, p->gp, p->pose_mask, w->L, w->y, w->scal);
     if (p->n_seg)
-        k_lm_segment_Z<<<grid_for(p->n_seg * 15, 256), 256, 0, st>>>(p->n_seg, nc, p->seg_cam, p->seg_pose, p->W, w->L,
-                                                                     p->cam_mask, p->pose_mask, w->Z);
+        k_lm_segment_Z<<<grid_for(p->n_seg * 15, 256), 256, 0, st>>>(p->n_seg, nc, p->seg_cam, p->seg_pose, p->W, w->L, w->y,
+                                                                     p->cam_mask, p->pose_mask, w->Z, rhs);
     PCS_CUDA(cudaGetLastError());
     const double minus1 = -1.0, one = 1.0, zero = 0.0;
     static const bool lib_syrk = [] { const char* e = std::getenv("PCS_LM_SYRK"); return e && e[0] == 'c'; }();   // A/B runs
     if (lib_syrk) PCS_BLAS(cublasDsyrk(w->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, &one, Smat, (int)nc));
     else PCS_TRY(launch_schur_syrk(st, p->sm_count, nc, np, w->Z, Smat));
-    PCS_BLAS(cublasDgemv(w->blas, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, w->y, 1, &one, rhs, 1));
     if (p->allreduce) {
         int rc = p->allreduce(p->allreduce_user, w->red, w->red_doubles, 0, (void*)st);
         if (rc != 0) { set_error("all-reduce callback failed"); return PCS_ERR_CUDA; }
