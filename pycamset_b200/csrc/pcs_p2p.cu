@@ -6,6 +6,8 @@
 // rank: write the local block into every peer's buffer (posted NVLink stores), raise a flag at every peer, wait for
 // every peer's flag, then add up the received blocks from local memory in rank order (bitwise identical result on
 // every rank).  Two data slots alternate so that a rank that races ahead never overwrites a block still being read.
+#include <cstdlib>
+
 #include "pcs_internal.cuh"
 
 namespace pcs {
@@ -75,6 +77,50 @@ k_p2p_allreduce(double* __restrict__ local, int64_t n, int rank, int world_rt, P
     }
 }
 
+// Multi-CTA form of the same protocol for larger worlds, where one SM pushing world * n doubles over NVLink is the
+// long pole: CTA b pushes the block to peer b (16-byte stores where the alignment allows) and raises this rank's flag
+// there; the CTAs of a rank tell each other through a counter in the rank's own buffer that they are done reading
+// `local`; every CTA then waits for all flags and sums its 1/world share of the entries.
+template <int WORLD>
+__global__ void __launch_bounds__(512)
+k_p2p_allreduce_multi(double* __restrict__ local, int64_t n, int rank, int world_rt, P2PPeers peers, uint64_t epoch)
+{
+    const int world = WORLD > 0 ? WORLD : world_rt;
+    const int tid = threadIdx.x, b = blockIdx.x;   // gridDim.x == world
+    const int64_t data = P2P_FLAG_DOUBLES + (int64_t)(epoch & 1) * world * n;
+    {
+        double* dst = peers.buf[b] + data + (int64_t)rank * n;
+        const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(local)) & 15) == 0;
+        const int64_t n2 = vec ? n / 2 : 0;
+        for (int64_t i = tid; i < n2; i += blockDim.x)
+            reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(local)[i];
+        for (int64_t i = 2 * n2 + tid; i < n; i += blockDim.x) dst[i] = local[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    double* mine = peers.buf[rank];
+    if (tid == 0) {
+        st_release_sys(reinterpret_cast<uint64_t*>(peers.buf[b]) + rank, epoch);   // my flag in peer b's buffer
+        atomicAdd(reinterpret_cast<unsigned long long*>(mine) + P2P_MAX_WORLD, 1ull);   // this CTA is done reading `local`
+    }
+    if (tid < world) {
+        const uint64_t* theirs = reinterpret_cast<const uint64_t*>(mine) + tid;     // peer tid's flag in mine
+        while (ld_acquire_sys(theirs) < epoch) { }
+    } else if (tid == world) {
+        const uint64_t* done = reinterpret_cast<const uint64_t*>(mine) + P2P_MAX_WORLD;
+        while (ld_acquire_sys(done) < epoch * (uint64_t)world) { }
+    }
+    __syncthreads();
+    const int64_t i0 = n * b / world, i1 = n * (b + 1) / world;
+    for (int64_t i = i0 + tid; i < i1; i += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+            if (r < world) s += ld_relaxed_sys(mine + data + (int64_t)r * n + i);   // rank order: identical bits everywhere
+        local[i] = s;
+    }
+}
+
 }  // namespace pcs
 
 using namespace pcs;
@@ -114,6 +160,14 @@ int pcs_p2p_allreduce_camera_blocks(pcs_problem* p)
     ++st->epoch;
     auto kern = st->world == 2 ? k_p2p_allreduce<2> : st->world == 4 ? k_p2p_allreduce<4> : st->world == 8 ? k_p2p_allreduce<8>
                                                                                                           : k_p2p_allreduce<0>;
+    // worlds of 8 and more use the multi-CTA form (PCS_P2P_MULTI=0/1 forces either one for A/B runs)
+    static const int force = [] { const char* e = std::getenv("PCS_P2P_MULTI"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    const bool multi = force >= 0 ? force == 1 : st->world >= 8;
+    if (multi) {
+        auto mk = st->world == 2 ? k_p2p_allreduce_multi<2> : st->world == 4 ? k_p2p_allreduce_multi<4>
+                  : st->world == 8 ? k_p2p_allreduce_multi<8> : k_p2p_allreduce_multi<0>;
+        mk<<<st->world, 512, 0, p->stream>>>(p->U, st->n, st->rank, st->world, st->peers, st->epoch);
+    } else
     kern<<<1, 1024, 0, p->stream>>>(p->U, st->n, st->rank, st->world, st->peers, st->epoch);
     PCS_CUDA(cudaGetLastError());
     ++p->n_launches;
