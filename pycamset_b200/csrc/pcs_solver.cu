@@ -4,9 +4,12 @@
 // (optimisation_handling.py:52-117).  The reference never forms J^T J; here the fused kernel delivers the
 // block normal equations and each LM step is
 //   template chain:  eliminate the pose blocks (batched 6x6 Cholesky), form the reduced camera system
-//                    S = U + lambda D_c - Z Z^T with Z = W L^-T (cuBLAS DSYRK on the dense (15C x 6M) Z),
-//                    [all-reduce S | rhs across ranks], dense Cholesky (cuSOLVER), back-substitute the poses;
-//   self-calibration: dense (n_free x n_free) normal matrix + Cholesky.
+//                    S = U + lambda D_c - Z Z^T with Z = W L^-T (k_schur_syrk, pcs_schur.cu; the dense (15C x 6M) Z
+//                    and the reduced right-hand side come from k_lm_segment_Z), [all-reduce S | rhs across ranks],
+//                    dense SPD solve (k_chol_solve, pcs_chol.cu; cuSOLVER for systems too large for it),
+//                    back-substitute the poses, move to the trial point and evaluate it with the full
+//                    normal-equation kernel into the second output set -- one host synchronisation per iteration;
+//   self-calibration: dense (n_free x n_free) normal matrix + cuSOLVER Cholesky, residual-only trial pass.
 // Marquardt scaling (lambda * diag(J^T J)) plays the role of x_scale='jac'; Nielsen's gain-ratio update
 // drives lambda.  Fixed parameters are rows / columns replaced by the identity.
 #include <cublas_v2.h>
@@ -333,16 +336,6 @@ __global__ void k_lm_gather_readback(const double* __restrict__ scal, const int*
     if (t < 8) out[t] = (t == 6 && cost_trial) ? *cost_trial : scal[t];
     if (t == 8) out[8] = (double)*info;
     if (t == 9) out[9] = *cost_lin;
-}
-
-__global__ void k_max_abs(int64_t n, const double* __restrict__ v, double* __restrict__ out)
-{
-    double m = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        m = fmax(m, fabs(v[i]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(m));
 }
 
 // dense path: Hd = H + lambda diag(H), rhs = -g ; pred / norms after the solve
