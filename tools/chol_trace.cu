@@ -31,6 +31,7 @@ int main(int argc, char** argv)
         if (ms < best) best = ms;
     }
     printf("best of 20 (incl. 2 memsets): %.1f us\n", best * 1e3);
+    cudaMemset(info, 0, 4);   // the warm-up solves re-factor an already factored matrix and raise it
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice); cudaMemcpy(db, b.data(), n * 8, cudaMemcpyHostToDevice);
         cudaEventRecord(e0);
