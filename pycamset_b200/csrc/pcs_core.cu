@@ -773,11 +773,7 @@ int pcs_jacobian_values_dev(pcs_problem* p, const double* x_dev, double* vals_de
                                                       p->posetab, p->dRtab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
                                                       p->row_prefix, p->C, vals_dev);
     } else {
-        static bool attr_set = false;
-        if (!attr_set) {
-            PCS_CUDA(cudaFuncSetAttribute(k_jacobian<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
+        PCS_CUDA(ensure_dynamic_smem(k_jacobian<24>, smem));
         k_jacobian<24><<<grid, 128, smem, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab,
                                                       p->posetab, p->dRtab, points_ptr(p), p->cam_mask, p->pose_mask, p->key_mask,
                                                       p->row_prefix, p->C, vals_dev);

@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pcs_b200.h"
@@ -29,6 +32,24 @@ void set_error(const std::string& msg);
             return PCS_ERR_INVALID;                             \
         }                                                       \
     } while (0)
+
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device, once per (kernel, device): the attribute
+// belongs to the device's context, so a process that drives several GPUs has to set it on each of them.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[{reinterpret_cast<const void*>(kernel), dev}];
+    if (have >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
 
 #define PCS_TRY(expr)              \
     do {                           \

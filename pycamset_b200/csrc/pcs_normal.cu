@@ -492,12 +492,8 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     static const int cfg = [] { const char* e = std::getenv("PCS_NE_CFG"); return e && e[0] >= '0' && e[0] <= '5' ? e[0] - '0' : 3; }();
     const int ctas = cfg == 3 ? 5 : cfg == 5 ? 3 : 4, warps = 4, opl = cfg >= 4 ? 2 : 1;
     auto kern = cfg == 0 ? k_normal<4, 4, 1> : cfg == 4 ? k_normal<4, 4, 2> : cfg == 5 ? k_normal<3, 4, 2> : k_normal<5, 4, 1>;
-    static bool attr_set = false;
     const size_t smem = (size_t)warps * NE_WARP_DOUBLES * sizeof(double);
-    if (!attr_set) {
-        PCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    PCS_CUDA(ensure_dynamic_smem(kern, smem));
     // persistent-style grid: `ctas` CTAs of `warps` warps per SM; at least ~64 observations per warp
     const int64_t n_part_obs = p->N / n_parts + 1;
     int64_t n_warps = std::min<int64_t>((n_part_obs + 64 * opl - 1) / (64 * opl), (int64_t)p->sm_count * ctas * warps);

@@ -185,11 +185,7 @@ int launch_schur_syrk(cudaStream_t st, int sm_count, int64_t n, int64_t k, const
     const size_t smem = (size_t)S_STAGES * STAGE_DOUBLES * sizeof(double);
     const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(Z) & 15) == 0);
     auto kern = aligned ? k_schur_syrk<true> : k_schur_syrk<false>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[aligned]) {
-        PCS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[aligned] = true;
-    }
+    PCS_CUDA(ensure_dynamic_smem(kern, smem));
     const int64_t units = (int64_t)n_lower * n_slabs;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)sm_count, units));   // two CTAs per SM
     kern<<<grid, S_THREADS, smem, st>>>(n, k, Z, S, n_lower, n_slabs);
