@@ -54,6 +54,7 @@ struct LmWorkspace {
     // one pinned read-back per iteration: scal[8] | info | cost of the linearisation point (gathered on the device)
     double* h_read = nullptr;   // pinned [10]
     double* d_read = nullptr;   // [10]
+    double* comb = nullptr;     // [5 + world] multi-rank: the step scalars of all ranks in ONE sum all-reduce (see k_lm_pack_scalars)
     // dense path
     double* H = nullptr;     // [n_free^2 + n_free + 1] = JtJ | Jtr | cost  (aliases p->dense)
     double* Hd = nullptr;    // damped copy [n_free^2]
@@ -328,12 +329,37 @@ __global__ void k_lm_take_step(int64_t L, int64_t nc, const double* __restrict__
     if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax((unsigned long long*)(scal + 4), (unsigned long long)__double_as_longlong(m));
 }
 
-// everything the host reads after an iteration, gathered into one buffer: scal[0..7] | info | cost of the linearisation
+// Multi-rank: everything that has to be combined across ranks after the trial evaluation goes into ONE sum all-reduce:
+// comb = [pred | |dx|^2 | |x|^2 | trial cost | pose-factorisation failure flag | per-rank slots of the pose gradient
+// inf-norm (own slot set, others 0)]; after the sum every rank holds all the norms and takes their maximum, and a
+// failure on any rank is seen by all of them, so the ranks take the same branch (k_lm_gather_readback).
+__global__ void k_lm_pack_scalars(const double* __restrict__ scal, const double* __restrict__ cost_trial, int rank, int world,
+                                  double* __restrict__ comb)
+{
+    const int t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t < 3) comb[t] = scal[t];
+    else if (t == 3) comb[3] = *cost_trial;
+    else if (t == 4) comb[4] = scal[5];
+    else if (t < 5 + world) comb[t] = (t - 5 == rank) ? scal[3] : 0.0;
+}
+
+// everything the host reads after an iteration, gathered into one buffer: scal[0..7] | info | cost of the linearisation.
+// comb != nullptr: the all-reduced scalars of k_lm_pack_scalars replace the rank-local ones.
 __global__ void k_lm_gather_readback(const double* __restrict__ scal, const int* __restrict__ info, const double* __restrict__ cost_lin,
-                                     const double* __restrict__ cost_trial, double* __restrict__ out)
+                                     const double* __restrict__ cost_trial, const double* __restrict__ comb, int world,
+                                     double* __restrict__ out)
 {
     const int t = threadIdx.x;
-    if (t < 8) out[t] = (t == 6 && cost_trial) ? *cost_trial : scal[t];
+    if (t < 8) {
+        double v = scal[t];
+        if (comb) {
+            if (t < 3) v = comb[t];
+            else if (t == 3) { v = 0.0; for (int r = 0; r < world; ++r) v = fmax(v, comb[5 + r]); }
+            else if (t == 5) v = comb[4];
+            else if (t == 6) v = comb[3];
+        } else if (t == 6 && cost_trial) v = *cost_trial;
+        out[t] = v;
+    }
     if (t == 8) out[8] = (double)*info;
     if (t == 9) out[9] = *cost_lin;
 }
@@ -401,6 +427,7 @@ void lm_free(pcs_problem* p)
     if (w->bar) cudaFree(w->bar);
     if (w->h_read) cudaFreeHost(w->h_read);
     if (w->d_read) cudaFree(w->d_read);
+    if (w->comb) cudaFree(w->comb);
     delete w;
     p->lm_ws = nullptr;
 }
@@ -419,6 +446,7 @@ static int lm_prepare(pcs_problem* p)
     PCS_CUDA(cudaMalloc((void**)&w->scal, 8 * 8));
     PCS_CUDA(cudaMalloc((void**)&w->info, sizeof(int)));
     PCS_CUDA(cudaMalloc((void**)&w->d_read, 10 * 8));
+    PCS_CUDA(cudaMalloc((void**)&w->comb, (size_t)(5 + std::max(p->world, 1)) * 8));
     PCS_CUDA(cudaMallocHost((void**)&w->h_read, 10 * 8));
     PCS_CUDA(cudaMemsetAsync(w->delta, 0, (size_t)p->L * 8, p->stream));
     if (p->chain == PCS_CHAIN_TEMPLATE) {
@@ -508,17 +536,8 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     k_lm_assemble_delta<<<grid_for(15 * (int64_t)p->C + 6 * (int64_t)p->M, 128), 128, 0, st>>>(
         p->C, p->M, lambda, rhs, dp, p->U, p->gc, p->V, p->gp, p->cam_mask, p->pose_mask, p->params, w->delta, w->scal, p->rank == 0);
     PCS_CUDA(cudaGetLastError());
-    if (p->allreduce) {  // pred, |dx|^2, |x|^2 are partial sums over this rank's poses; the pose gradient norm is a max
-        if (p->allreduce(p->allreduce_user, w->scal, 3, 0, (void*)st) != 0 ||
-            p->allreduce(p->allreduce_user, w->scal + 3, 1, 1, (void*)st) != 0) {
-            set_error("all-reduce callback failed");
-            return PCS_ERR_CUDA;
-        }
-    }
-    return PCS_OK;
+    return PCS_OK;   // multi-rank: pred, |dx|^2, |x|^2 and the pose gradient norm are still rank-local here (k_lm_pack_scalars)
 }
-
-__global__ void k_copy_double(const double* __restrict__ src, double* __restrict__ dst) { *dst = *src; }
 
 }  // namespace pcs
 
@@ -590,17 +609,17 @@ int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in
             swap_normal_buffers(p, w);
             rc = eval_lin();
             if (rc != PCS_OK) break;
-            const double* trial_cost = p->cost;
-            if (p->allreduce) {   // the trial cost is a partial sum: combine a copy (p->cost itself feeds the next reduction)
-                k_copy_double<<<1, 1, 0, st>>>(p->cost, w->scal + 6);
-                if (p->allreduce(p->allreduce_user, w->scal + 6, 1, 0, (void*)st) != 0) {
+            const double* comb = nullptr;
+            if (p->allreduce) {   // one combined all-reduce of the step scalars and the trial cost
+                k_lm_pack_scalars<<<grid_for(5 + p->world, 64), 64, 0, st>>>(w->scal, p->cost, p->rank, p->world, w->comb);
+                if (p->allreduce(p->allreduce_user, w->comb, 5 + p->world, 0, (void*)st) != 0) {
                     set_error("all-reduce callback failed");
                     rc = PCS_ERR_CUDA;
                     break;
                 }
-                trial_cost = nullptr;
+                comb = w->comb;
             }
-            k_lm_gather_readback<<<1, 32, 0, st>>>(w->scal, w->info, gcopy + w->nc, trial_cost, w->d_read);
+            k_lm_gather_readback<<<1, 32, 0, st>>>(w->scal, w->info, gcopy + w->nc, p->cost, comb, p->world, w->d_read);
             PCS_CUDA(cudaMemcpyAsync(w->h_read, w->d_read, 10 * 8, cudaMemcpyDeviceToHost, st));
             PCS_CUDA(cudaStreamSynchronize(st));
             std::memcpy(h_scal, w->h_read, 8 * 8);
