@@ -145,9 +145,10 @@ PCS_API int pcs_device_buffers_get(pcs_problem* p, pcs_device_buffers* out);
 
 /* Multi-GPU hook.  Observations are sharded by target pose: every rank owns the pose blocks of its poses and a
  * PARTIAL sum of the camera blocks.  pcs_lm_solve calls this callback (work enqueued on `stream`) to combine n
- * doubles in place across ranks: the Schur-reduced camera system [S | rhs | gc | cost] once per linear solve
- * (op 0 = sum) and a few scalars per step (op 0 = sum, op 1 = max).  The Python host installs a
- * torch.distributed (NCCL) all-reduce here; it must return 0 on success. */
+ * doubles in place across ranks: the Schur-reduced camera system [S | rhs | gc | cost] once per linear solve and
+ * one vector of 5 + world_size step scalars once per iteration (both op 0 = sum; op 1 = max is part of the contract
+ * but currently unused).  The Python host installs a torch.distributed (NCCL) all-reduce here; it must return 0 on
+ * success. */
 typedef int (*pcs_allreduce_fn)(void* user, double* buf_dev, int64_t n, int op, void* stream);
 PCS_API int pcs_set_allreduce(pcs_problem* p, pcs_allreduce_fn fn, void* user, int rank, int world_size);
 
@@ -165,8 +166,8 @@ PCS_API int pcs_costfn(pcs_problem* p, int n_tables, const double* im_points, co
  * peer memory -- the only exchange step of a pose-sharded normal-equation evaluation (C * 240 + 1 doubles, latency
  * bound).  Every rank allocates a zero-initialised buffer of pcs_p2p_buffer_bytes(p, world) that all peers have mapped
  * (e.g. torch.distributed._symmetric_memory) and passes the world's pointers, own buffer at index `rank`.
- * pcs_p2p_allreduce_camera_blocks enqueues one single-CTA kernel on the problem's stream; all ranks must call it the
- * same number of times.  No reference counterpart (the reference is single-process). */
+ * pcs_p2p_allreduce_camera_blocks enqueues one kernel on the problem's stream (a single CTA, or one CTA per peer for
+ * worlds of 8 and more); all ranks must call it the same number of times.  No reference counterpart (the reference is single-process). */
 PCS_API int64_t pcs_p2p_buffer_bytes(const pcs_problem* p, int world_size);
 PCS_API int pcs_p2p_allreduce_setup(pcs_problem* p, int rank, int world_size, void* const* peer_buffers, int64_t buffer_bytes);
 PCS_API int pcs_p2p_allreduce_camera_blocks(pcs_problem* p);
