@@ -415,10 +415,21 @@ __global__ void k_gather_free(int64_t n, const int32_t* __restrict__ free_idx, c
     if (j < n) x[j] = params[free_idx[j]];
 }
 
+// the two sets of normal-equation outputs [U | gc | cost | pad | V | gp | W] trade places
+static void swap_normal_buffers(pcs_problem* p, LmWorkspace* w)
+{
+    double* other = (p->ne == w->ne_orig) ? w->ne_alt : w->ne_orig;
+    const int64_t o_gc = p->gc - p->ne, o_cost = p->cost - p->ne, o_V = p->V - p->ne, o_gp = p->gp - p->ne, o_W = p->W - p->ne;
+    p->ne = other; p->U = other; p->gc = other + o_gc; p->cost = other + o_cost; p->V = other + o_V; p->gp = other + o_gp;
+    p->W = other + o_W;
+}
+
 void lm_free(pcs_problem* p)
 {
     LmWorkspace* w = (LmWorkspace*)p->lm_ws;
     if (!w) return;
+    // a solve that returned early on an error may have left the problem on the second output set
+    if (w->ne_alt && w->ne_orig && p->ne == w->ne_alt) swap_normal_buffers(p, w);
     if (w->blas) cublasDestroy(w->blas);
     if (w->solver) cusolverDnDestroy(w->solver);
     double* ptrs[] = {w->L, w->y, w->Z, w->red, w->t, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs, w->Ldiag, w->ne_alt};
@@ -486,15 +497,6 @@ static int eval_normal(pcs_problem* p)
     return launch_normal_blocks(p, true);
 }
 
-// the two sets of normal-equation outputs [U | gc | cost | pad | V | gp | W] trade places
-static void swap_normal_buffers(pcs_problem* p, LmWorkspace* w)
-{
-    double* other = (p->ne == w->ne_orig) ? w->ne_alt : w->ne_orig;
-    const int64_t o_gc = p->gc - p->ne, o_cost = p->cost - p->ne, o_V = p->V - p->ne, o_gp = p->gp - p->ne, o_W = p->W - p->ne;
-    p->ne = other; p->U = other; p->gc = other + o_gc; p->cost = other + o_cost; p->V = other + o_V; p->gp = other + o_gp;
-    p->W = other + o_W;
-}
-
 // One damped solve at the current linearisation, enqueued without synchronising.  Afterwards w->delta holds the step
 // (parameter-string layout), w->scal = {pred, |dx|^2, |x|^2, |g_pose|_inf, |g_cam|_inf, flag, trial cost, -},
 // w->info the factorisation status and cost_r (inside w->red) the all-reduced r.r of the linearisation point.
@@ -559,7 +561,7 @@ void pcs_lm_default_options(pcs_lm_options* o)
 // dense normal equations at the current parameters, device-resident (pcs_core.cu)
 int pcs_normal_dense_dev_internal(pcs_problem* p);
 
-int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in, double* x_out, pcs_lm_stats* stats)
+static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in, double* x_out, pcs_lm_stats* stats)
 {
     PCS_REQUIRE(p && x_out, "NULL argument");
     PCS_CUDA(cudaSetDevice(p->device));
@@ -723,6 +725,16 @@ int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in
         stats->cost_initial = 0.5 * cost0; stats->cost_final = 0.5 * cost; stats->grad_norm_inf = ginf;
         stats->lambda_final = lambda; stats->seconds = ms * 1e-3;
     }
+    return rc;
+}
+
+int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in, double* x_out, pcs_lm_stats* stats)
+{
+    const int rc = lm_solve_impl(p, x0, opts_in, x_out, stats);
+    // an error return in the middle of an iteration can leave the problem on the second output set: callers hold
+    // pointers into the original one (pcs_device_buffers_get), so the problem always leaves on it
+    LmWorkspace* w = p ? (LmWorkspace*)p->lm_ws : nullptr;
+    if (w && w->ne_alt && w->ne_orig && p->ne == w->ne_alt) swap_normal_buffers(p, w);
     return rc;
 }
 
