@@ -54,6 +54,7 @@ struct LmWorkspace {
     // one pinned read-back per iteration: scal[8] | info | cost of the linearisation point (gathered on the device)
     double* h_read = nullptr;   // pinned [10]
     double* d_read = nullptr;   // [10]
+    int comb_cap = 0;
     double* comb = nullptr;     // [5 + world] multi-rank: the step scalars of all ranks in ONE sum all-reduce (see k_lm_pack_scalars)
     // dense path
     double* H = nullptr;     // [n_free^2 + n_free + 1] = JtJ | Jtr | cost  (aliases p->dense)
@@ -457,7 +458,6 @@ static int lm_prepare(pcs_problem* p)
     PCS_CUDA(cudaMalloc((void**)&w->scal, 8 * 8));
     PCS_CUDA(cudaMalloc((void**)&w->info, sizeof(int)));
     PCS_CUDA(cudaMalloc((void**)&w->d_read, 10 * 8));
-    PCS_CUDA(cudaMalloc((void**)&w->comb, (size_t)(5 + std::max(p->world, 1)) * 8));
     PCS_CUDA(cudaMallocHost((void**)&w->h_read, 10 * 8));
     PCS_CUDA(cudaMemsetAsync(w->delta, 0, (size_t)p->L * 8, p->stream));
     if (p->chain == PCS_CHAIN_TEMPLATE) {
@@ -579,6 +579,13 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
         std::memcpy(p->h_pin, x0, (size_t)p->n_free * 8);
         PCS_CUDA(cudaMemcpyAsync(p->x, p->h_pin, (size_t)p->n_free * 8, cudaMemcpyHostToDevice, st));
         PCS_TRY(launch_scatter_x(p, p->x));
+    }
+    if (w->comb_cap < 5 + p->world) {   // the world size may have been set after the workspace was created
+        if (w->comb) cudaFree(w->comb);
+        w->comb = nullptr;
+        w->comb_cap = 0;
+        PCS_CUDA(cudaMalloc((void**)&w->comb, (size_t)(5 + p->world) * 8));
+        w->comb_cap = 5 + p->world;
     }
     const bool tmpl = p->chain == PCS_CHAIN_TEMPLATE;
     const int64_t n = p->n_free;
