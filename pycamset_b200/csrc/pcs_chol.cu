@@ -489,7 +489,8 @@ int chol_prepare(int device, int64_t n, double** Ldiag, unsigned long long** bar
     PCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     PCS_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     if (!coop || smem > (size_t)max_optin) return PCS_OK;
-    PCS_CUDA(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // monotone per (kernel, device): a later, smaller problem must not lower the opt-in of a live larger one
+    PCS_CUDA(ensure_dynamic_smem(k_chol_solve, smem));
     int per_sm = 0;
     PCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_solve, CHOL_THREADS, smem));
     if (per_sm < 1) return PCS_OK;

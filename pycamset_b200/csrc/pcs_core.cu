@@ -601,7 +601,6 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     BUILD_TRY(dev_alloc(&p->s_uv, 2 * N)); BUILD_TRY(dev_alloc(&seg_scan, N));
     int64_t n_seg = 0;
     if (N > 0) {
-        PCS_REQUIRE(N < ((int64_t)1 << 31), "n_obs must be below 2^31 per problem (shard by pose across GPUs)");
         need = tmp_bytes;
         BUILD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, need, keys_a, keys_b, idx_a, idx_b, N, 0, key_bits, st));
         k_segment_flags<<<grid_for(N, 256), 256, 0, st>>>(N, keys_b, flags);
@@ -649,6 +648,7 @@ int pcs_problem_create(const pcs_problem_desc* d, pcs_problem** out)
         return PCS_ERR_CHAIN;
     }
     PCS_REQUIRE(d->n_obs >= 0 && d->n_cams > 0 && d->n_poses > 0 && d->n_keys > 0, "sizes must be positive");
+    PCS_REQUIRE(d->n_obs < ((int64_t)1 << 31), "n_obs must be below 2^31 per problem (shard by pose across GPUs)");
     PCS_REQUIRE(d->n_obs == 0 || (d->cam && d->pose && d->key && d->uv), "observation arrays are NULL");
     PCS_REQUIRE(d->chain != PCS_CHAIN_TEMPLATE || d->template_xyz, "template chain needs template_xyz");
     int n_dev = 0;

@@ -61,22 +61,29 @@ k_costfn_per_image(int64_t N, const int32_t* __restrict__ s_cam, const int32_t* 
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int b = blockIdx.y, lane = threadIdx.x & 31;
-    int m = -1;
+    int m = -1, c = -1;
     double v = 0.0;
     if (i < N) {
         m = s_pose[i];
-        const double2 e = costfn_one(t, b, s_cam[i], m, s_key[i], s_uv[i]);
+        c = s_cam[i];
+        const double2 e = costfn_one(t, b, c, m, s_key[i], s_uv[i]);
         v = sqrt(e.x * e.x + e.y * e.y);
     }
-    // segmented suffix sum over runs of equal pose inside the warp; the first lane of a run owns the total
+    // Segmented suffix sum over the warp's runs of ADJACENT lanes with the same (camera, pose) key; the first lane of
+    // a run owns the total.  The table is (camera, pose)-sorted, so one pose recurs once per camera: runs are
+    // delimited by adjacency (head flags), never by pose equality at a distance -- two runs of the same pose that
+    // land in one warp (few observations per pair) stay separate sums.
+    const int mp = __shfl_up_sync(0xffffffffu, m, 1), cp = __shfl_up_sync(0xffffffffu, c, 1);
+    const bool head = lane == 0 || mp != m || cp != c;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));   // heads of later runs
+    const int run_end = above ? __ffs(above) - 1 : 32;               // one past the last lane of this lane's run
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const double w = __shfl_down_sync(0xffffffffu, v, off);
-        const int mo = __shfl_down_sync(0xffffffffu, m, off);
-        if (lane + off < 32 && mo == m) v += w;
+        if (lane + off < run_end) v += w;
     }
-    const int mp = __shfl_up_sync(0xffffffffu, m, 1);
-    if (m >= 0 && (lane == 0 || mp != m)) atomicAdd(per_image + (int64_t)b * t.M + m, v);
+    if (m >= 0 && head) atomicAdd(per_image + (int64_t)b * t.M + m, v);
 }
 
 }  // namespace pcs

@@ -60,6 +60,7 @@ struct LmWorkspace {
     double* H = nullptr;     // [n_free^2 + n_free + 1] = JtJ | Jtr | cost  (aliases p->dense)
     double* Hd = nullptr;    // damped copy [n_free^2]
     double* rhs = nullptr;   // [n_free]
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of a solve (owned by the workspace: no leak on error returns)
 };
 
 #define PCS_BLAS(call)                                                                       \
@@ -440,15 +441,29 @@ void lm_free(pcs_problem* p)
     if (w->h_read) cudaFreeHost(w->h_read);
     if (w->d_read) cudaFree(w->d_read);
     if (w->comb) cudaFree(w->comb);
+    if (w->ev0) cudaEventDestroy(w->ev0);
+    if (w->ev1) cudaEventDestroy(w->ev1);
     delete w;
     p->lm_ws = nullptr;
 }
 
+static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w);
+
+// The workspace is published on the problem only after every allocation succeeded; a failure half-way (out of memory
+// for Z, n_free over the dense limit, ...) frees what was built, so that the next call starts from scratch instead of
+// launching on NULL buffers.
 static int lm_prepare(pcs_problem* p)
 {
     if (p->lm_ws) return PCS_OK;
     LmWorkspace* w = new LmWorkspace();
     p->lm_ws = w;
+    const int rc = lm_prepare_impl(p, w);
+    if (rc != PCS_OK) lm_free(p);
+    return rc;
+}
+
+static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
+{
     PCS_BLAS(cublasCreate(&w->blas));
     PCS_BLAS(cublasSetStream(w->blas, p->stream));
     PCS_SOLVER(cusolverDnCreate(&w->solver));
@@ -460,6 +475,8 @@ static int lm_prepare(pcs_problem* p)
     PCS_CUDA(cudaMalloc((void**)&w->d_read, 10 * 8));
     PCS_CUDA(cudaMallocHost((void**)&w->h_read, 10 * 8));
     PCS_CUDA(cudaMemsetAsync(w->delta, 0, (size_t)p->L * 8, p->stream));
+    PCS_CUDA(cudaEventCreate(&w->ev0));
+    PCS_CUDA(cudaEventCreate(&w->ev1));
     if (p->chain == PCS_CHAIN_TEMPLATE) {
         w->nc = 15 * (int64_t)p->C;
         w->np = 6 * (int64_t)p->M;
@@ -567,12 +584,16 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
     PCS_CUDA(cudaSetDevice(p->device));
     pcs_lm_options o;
     if (opts_in) o = *opts_in; else pcs_lm_default_options(&o);
+    if (p->chain == PCS_CHAIN_SELFCAL && p->world > 1) {
+        // the dense self-calibration system is not combined across ranks: refuse instead of letting the replicated
+        // camera / point parameters diverge silently
+        set_error("pcs_lm_solve: the self-calibration chain is single-rank (world_size > 1 is supported for the template chain)");
+        return PCS_ERR_UNSUPPORTED;
+    }
     PCS_TRY(lm_prepare(p));
     LmWorkspace* w = (LmWorkspace*)p->lm_ws;
     cudaStream_t st = p->stream;
-    cudaEvent_t ev0, ev1;
-    PCS_CUDA(cudaEventCreate(&ev0));
-    PCS_CUDA(cudaEventCreate(&ev1));
+    cudaEvent_t ev0 = w->ev0, ev1 = w->ev1;
     PCS_CUDA(cudaEventRecord(ev0, st));
     if (x0) {
         PCS_TRY(ensure_pinned(p, std::max<int64_t>(p->n_free, 1)));
@@ -725,8 +746,6 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
     PCS_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     if (stats) {
         stats->iterations = it; stats->n_eval_normal = n_normal; stats->n_eval_cost = n_cost; stats->status = status;
         stats->cost_initial = 0.5 * cost0; stats->cost_final = 0.5 * cost; stats->grad_norm_inf = ginf;

@@ -121,3 +121,50 @@ class P2PCameraAllReduce:
 
     def __call__(self):
         self.problem.p2p_allreduce_camera_blocks()
+
+
+def lm_solve_sharded(cam, pose, key, uv, n_cams, n_poses, n_keys, template, params, unfixed, *, device=None, group=None,
+                     max_iter=100, ftol=1e-8, xtol=1e-8, gtol=1e-8, lambda0=1e-3, verbose=0):
+    """Pose-sharded Levenberg-Marquardt over the ranks of `group` (template chain), one process per GPU.
+
+    Every rank passes the SAME full problem (observation table in dd order, full parameter string, boolean `unfixed`
+    mask over it); the rank keeps only the observations of its contiguous pose range (balanced by observation count),
+    eliminates its own poses and all-reduces the Schur-reduced camera system over NCCL.  Returns
+    (params_out, stats): the FULL parameter string at the solution -- camera blocks are replicated, pose blocks are
+    all-gathered from their owners -- identical on every rank."""
+    import torch
+    import torch.distributed as dist
+    from .problem import BundleProblem
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        device = torch.cuda.current_device()
+    cam = np.asarray(cam); pose = np.asarray(pose); key = np.asarray(key); uv = np.asarray(uv).reshape(-1, 2)
+    params = np.asarray(params, np.float64)
+    unfixed = np.asarray(unfixed, bool)
+    ranges = balanced_pose_ranges(np.bincount(pose.astype(np.int64), minlength=n_poses), world)
+    s, e = ranges[rank]
+    c_s, p_s, k_s, uv_s = shard_observations(cam, pose, key, uv, (s, e))
+    par = shard_param_string(params, n_cams, n_poses, (s, e))
+    unf = shard_param_string(unfixed, n_cams, n_poses, (s, e)).astype(bool)
+    with BundleProblem(0, c_s, p_s, k_s, uv_s, n_cams, e - s, n_keys, template=template, unfixed=unf, device=device) as prob:
+        prob.set_param_string(par)
+        if world > 1:
+            install_nccl_allreduce(prob, group)
+        _, stats = prob.lm_solve(par[unf], max_iter=max_iter, ftol=ftol, xtol=xtol, gtol=gtol, lambda0=lambda0, verbose=verbose)
+        local = prob.get_param_string()
+    out = params.copy()
+    C15 = 15 * n_cams
+    out[:C15] = local[:C15]
+    if world > 1:
+        # pose rows travel as one padded all-gather (ranges differ by at most a few poses)
+        width = max(r[1] - r[0] for r in ranges) * 6
+        mine = torch.zeros(width, dtype=torch.float64, device=f"cuda:{device}")
+        mine[:6 * (e - s)] = torch.from_numpy(local[C15:]).to(mine.device)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        for r, (rs, re) in enumerate(ranges):
+            out[C15 + 6 * rs:C15 + 6 * re] = parts[r][:6 * (re - rs)].cpu().numpy()
+    else:
+        out[C15:C15 + 6 * n_poses] = local[C15:]
+    return out, stats

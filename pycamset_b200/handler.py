@@ -62,15 +62,16 @@ def unfixed_mask(bundle_primitive) -> np.ndarray:
 
 
 def detection_table(handler) -> np.ndarray:
-    """The flattened observation table `dd` (N x 5: cam, image, flat key, u, v) the reference closes over
-    (template_handler.py:163, target_detections.py:333-351)."""
-    if hasattr(handler, "get_detection_data"):
-        try:
-            return np.asarray(handler.get_detection_data(flatten=True), np.float64)
-        except TypeError:
-            pass
-    shape = handler.target.point_data.shape
-    return np.asarray(handler.detection.return_flattened_keys(shape[:-1]).get_data(), np.float64)
+    """The flattened observation table `dd` (N x 5: cam, image, flat key, u, v) exactly as the reference's closures
+    build it: `self.detection.return_flattened_keys(target_shape[:-1]).get_data()` -- UNFILTERED, i.e. rows of
+    `missing_poses` are kept (template_handler.py:160-163, :175; target_detections.py:333-351), so residual length and
+    row order equal those of the closures this module replaces.  `get_detection_data(flatten=True)` (which deletes the
+    rows of missing poses, :398-403) is only the fallback for handlers that expose no `detection` object."""
+    det = getattr(handler, "detection", None)
+    if det is not None and hasattr(det, "return_flattened_keys"):
+        shape = handler.target.point_data.shape
+        return np.asarray(det.return_flattened_keys(shape[:-1]).get_data(), np.float64)
+    return np.asarray(handler.get_detection_data(flatten=True), np.float64)
 
 
 def export_problem(handler) -> dict:

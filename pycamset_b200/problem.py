@@ -60,6 +60,8 @@ class BundleProblem:
                 keep.append(t)
                 return ct.c_void_p(t.data_ptr())
             n_obs = int(cam.shape[0])
+            if not (int(pose.shape[0]) == n_obs and int(key.shape[0]) == n_obs and int(uv.numel()) == 2 * n_obs):
+                raise ValueError("cam / pose / key / uv disagree on the number of observations")
             pc, pp, pk = prep(cam, torch.int32), prep(pose, torch.int32), prep(key, torch.int32)
             pu = prep(uv.reshape(-1), torch.float64)
             torch.cuda.synchronize(device)

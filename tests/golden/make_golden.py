@@ -192,13 +192,47 @@ def ccube_goldens():
     dump_case("ccube_selfcal", sh, x_s, extra=dict(fixed_inds=np.asarray(sh.fixed_inds, np.int32)))
 
 
+def ccube_selfcal_final():
+    """Config 3 at the reference's FINAL iterate: tests/self_calibrate_ccube_test.py:23-37 verbatim (SelfBundleHandler
+    from the template calibration, max_nfev 100, run_bundle_adjustment), dumping the solver's x, cost, nfev and the mean
+    reprojection error the reference's own test thresholds (< 0.50 px).  Written to ccube_selfcal_final.npz; the
+    start point is asserted to be the `x` of ccube_selfcal.npz."""
+    from pyCamSet import calibrate_cameras, Ccube
+    from pyCamSet.optimisation.standard_bundle_handler import SelfBundleHandler
+    from pyCamSet.optimisation.optimisation_handling import run_bundle_adjustment
+    import cv2
+    import time
+
+    loc = Path("/root/reference/tests/test_data/calibration_ccube")
+    target = Ccube(n_points=10, length=40, aruco_dict=cv2.aruco.DICT_6X6_1000, border_fraction=0.2)
+    cams = calibrate_cameras(f_loc=loc, calibration_target=target, draw=False, save=False,
+                             problem_options={"outliers": "n", "verbosity": 0})
+    sh = SelfBundleHandler(detection=cams.calibration_handler.detection, target=target, camset=cams,
+                           options={"outliers": "n", "verbosity": 0, "max_nfev": 100})
+    sh.set_from_templated_camset(cams)
+    x0 = np.asarray(sh.get_initial_params()).copy()
+    g = np.load(HERE / "ccube_selfcal.npz")
+    assert np.max(np.abs(x0 - g["x"])) < 1e-9, "start point differs from the committed golden"
+    t0 = time.time()
+    res, _ = run_bundle_adjustment(param_handler=sh, threads=os.cpu_count())
+    dt = time.time() - t0
+    px = float(np.mean(np.linalg.norm(np.reshape(res.fun, (-1, 2)), axis=1)))
+    np.savez_compressed(HERE / "ccube_selfcal_final.npz", x_final=res.x, final_px=np.float64(px), cost_final=np.float64(res.cost),
+                        nfev=np.int32(res.nfev), status=np.int32(res.status), seconds=np.float64(dt))
+    print(f"[golden] ccube_selfcal_final: nfev={res.nfev} status={res.status} cost={res.cost:.6f} px={px:.6f} ({dt:.1f} s)")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-ccube", action="store_true")
     ap.add_argument("--only-costfn", action="store_true")
+    ap.add_argument("--selfcal-final", action="store_true", help="only (re)generate ccube_selfcal_final.npz")
     args = ap.parse_args()
     import pyCamSet
     assert "baseline/_ref" in pyCamSet.__file__, pyCamSet.__file__
+    if args.selfcal_final:
+        ccube_selfcal_final()
+        return 0
     costfn_golden()
     if args.only_costfn:
         return 0

@@ -126,3 +126,32 @@ def test_invalid_input_raises():
     with BundleProblem(1, rig.cam.numpy(), pose, key, uv, 4, 6, 81) as p:                  # self-calibration chain
         with pytest.raises(_lib.PcsError, match="template chain"):
             p.normal_equations()
+
+
+def test_lm_alternating_problem_sizes_keep_the_cholesky_shared_memory_optin():
+    """A small problem solved between two solves of a live larger one must not lower the dynamic shared-memory opt-in
+    of the persistent Cholesky kernel (n = 480 needs ~168 KB; the attribute is per kernel and device, not per problem)."""
+    from pycamset_b200 import synthetic as syn
+    from pycamset_b200.problem import BundleProblem
+
+    def make(C, M, seed):
+        rig = syn.make_rig(C, M, distortion=True, seed=seed, detect_prob=0.9)
+        intr, extr, poses = rig.perturbed(np.random.default_rng(seed), 1e-3)
+        params = rig.param_string(intr, extr, poses)
+        unfixed = np.ones(params.shape[0], bool)
+        unfixed[15 * C:15 * C + 6] = False
+        p = BundleProblem(0, rig.cam.numpy(), rig.pose.numpy(), rig.key.numpy(), rig.uv.numpy(), C, M, 81,
+                          template=rig.template, unfixed=unfixed)
+        p.set_param_string(params)
+        return p, params[unfixed]
+
+    big, xb = make(32, 6, 1)
+    small, xs = make(4, 6, 2)
+    try:
+        for _ in range(2):
+            _, st = big.lm_solve(xb, max_iter=3)
+            assert st["cost_final"] < st["cost_initial"]
+            _, st = small.lm_solve(xs, max_iter=3)
+            assert st["cost_final"] < st["cost_initial"]
+    finally:
+        big.close(); small.close()

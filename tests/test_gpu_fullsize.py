@@ -1,5 +1,9 @@
-"""GPU, BASELINE.json config 4 at full size (32-camera ring x 2000 poses, ~2.6 M observations): size-independent
-properties of the fused normal-equation kernel, checked against independent device paths.
+"""GPU, BASELINE.json config 4 at full size (32-camera ring x 2000 poses, ~2.6 M observations).
+
+PRIMARY check: every output of the fused normal-equation kernel (U, V, W, g_c, g_m, r.r) and of the residual kernel
+against the CPU ORACLE (oracle/ba_oracle.c) on the full 2.59 M-observation table.
+
+Secondary, size-independent properties of the fused kernel against independent device paths:
 
   * r.r from K_ne equals the sum of squares of the residual kernel's output;
   * U / V / W / g_c / g_m equal the corresponding blocks of the DENSE J^T J / J^T r accumulated by a different
@@ -96,3 +100,31 @@ def test_full_size_order_invariance_and_linearity(ring32):
         s = parts[0][0][k] + parts[1][0][k]
         assert np.max(np.abs(ne[k] - s)) <= 1e-11 * np.max(np.abs(ne[k])), k
     assert abs(ne["cost"] - parts[0][0]["cost"] - parts[1][0]["cost"]) <= 1e-12 * ne["cost"]
+
+
+def test_full_size_blocks_and_residual_against_the_oracle(ring32):
+    """Config 4 at full size against the CPU oracle (not against another kernel of this library): residual abs <= 1e-9 px,
+    block entries <= 1e-9 sqrt(d_a d_b), gradients <= 1e-9 sqrt(d_a cost), cost rel <= 1e-11."""
+    from oracle import oracle as orc
+    rig, params, unfixed = ring32
+    cam, pose, key, uv = (t.cpu().numpy() for t in (rig.cam, rig.pose, rig.key, rig.uv))
+    C, M = 32, 2000
+    o = orc.Problem(0, cam, pose, key, uv, C, M, 81, rig.template)
+    with _problem(rig, unfixed) as p:
+        p.set_param_string(params)
+        ne = p.normal_equations()
+        r = p.residual()
+        sc, sp, sl = p.segments()
+    r_o = o.residual(params)
+    assert r.shape == r_o.shape and np.max(np.abs(r - r_o)) < 1e-9
+    pair = cam.astype(np.int64) * M + pose
+    uniq, seg = np.unique(pair, return_inverse=True)
+    assert np.array_equal(sc.astype(np.int64) * M + sp, uniq)
+    U, gc, V, gp, W, cost = o.normal_blocks(params, seg.astype(np.int32), len(uniq))
+    assert abs(ne["cost"] - cost) <= 1e-11 * cost and abs(cost - float(r_o @ r_o)) <= 1e-11 * cost
+    dU = np.einsum("cii->ci", U); dV = np.einsum("mii->mi", V)
+    assert _scaled_close(ne["U"], U, dU, dU)
+    assert _scaled_close(ne["V"], V, dV, dV)
+    assert _scaled_close(ne["W"], W, dU[sc], dV[sp])
+    assert np.max(np.abs(ne["gc"] - gc) / np.sqrt(np.maximum(dU, 1e-300) * cost)) < 1e-9
+    assert np.max(np.abs(ne["gp"] - gp) / np.sqrt(np.maximum(dV, 1e-300) * cost)) < 1e-9
