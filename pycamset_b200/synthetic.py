@@ -231,9 +231,12 @@ def make_rig(n_cams: int, n_poses: int, *, layout: str = "ring", distortion: boo
     normal = torch.tensor([0.0, 0.0, -1.0], **f64)           # board front face (seen by camera 0 at pose 0)
     gen = torch.Generator(device=dev)
     cams, pss, keys, uvs = [], [], [], []
-    for m0 in range(pose_start, pose_stop, pose_chunk):
-        m1 = min(pose_stop, m0 + pose_chunk)
-        P = torch.as_tensor(poses[m0:m1], **f64)
+    # Chunks are aligned to multiples of `pose_chunk` of the GLOBAL pose axis and always generated in full, then cut
+    # to [pose_start, pose_stop): the random draws (detection mask, pixel noise) of a pose therefore do not depend on
+    # how the poses are sharded, and the union of the shards of any world size is the same table.
+    for c0 in range((pose_start // pose_chunk) * pose_chunk, pose_stop, pose_chunk):
+        c1 = min(n_poses, c0 + pose_chunk)
+        P = torch.as_tensor(poses[c0:c1], **f64)
         Rm = _rodrigues_t(P[:, :3])                          # (m,3,3)
         Xw = torch.einsum("mab,kb->mka", Rm, T) + P[:, None, 3:]          # (m,K,3)
         Xc = torch.einsum("cab,mkb->cmka", Rc, Xw) + tc[:, None, None, :]  # (C,m,K,3)
@@ -241,11 +244,16 @@ def make_rig(n_cams: int, n_poses: int, *, layout: str = "ring", distortion: boo
         n_c = torch.einsum("cab,mb->cma", Rc, torch.einsum("mab,b->ma", Rm, normal))  # (C,m,3)
         facing = (n_c[:, :, None, :] * Xc).sum(-1) < 0
         vis = facing & (Xc[..., 2] > 0.02) & (uv[..., 0] >= 0) & (uv[..., 0] <= 1000.0) & (uv[..., 1] >= 0) & (uv[..., 1] <= 1000.0)
-        gen.manual_seed(seed * 1000003 + m0)
+        gen.manual_seed(seed * 1000003 + c0)
         if detect_prob < 1.0:
             vis &= torch.rand(vis.shape, generator=gen, device=dev) < detect_prob
         noise = torch.randn(uv.shape, generator=gen, **f64) * noise_px
         uv = uv + noise
+        m0, m1 = max(c0, pose_start), min(c1, pose_stop)
+        if m0 >= m1:
+            continue
+        vis = vis[:, m0 - c0:m1 - c0]
+        uv = uv[:, m0 - c0:m1 - c0]
         if order == "pose":
             vis = vis.permute(1, 0, 2)
             uv = uv.permute(1, 0, 2, 3)

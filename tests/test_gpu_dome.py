@@ -49,7 +49,13 @@ def test_dome128_kernels_against_the_oracle():
     assert np.max(np.abs(r - o.residual(params))) < 1e-9
     col_o, rp_o = o.csr_structure(fm)
     assert np.array_equal(col, col_o) and np.array_equal(rp, rp_o)
-    assert rel_err(vals, o.csr_values(params, fm, rp_o)) < 1e-9
+    ref = o.csr_values(params, fm, rp_o)
+    # Entries many orders below the largest entry of their own row are products of cancellation in the OpenCV dR/dr
+    # formula both sides evaluate (worst case here: -5.3e-6 in a row whose largest entry is 2.5e3); their error is bounded
+    # relative to the row scale, not to themselves: |d| <= 1e-9 max(|ref|, 1e-8 rowmax).
+    rowmax = np.maximum.reduceat(np.abs(ref), rp_o[:-1])
+    floor = np.repeat(rowmax, np.diff(rp_o)) * 1e-8
+    assert np.max(np.abs(vals - ref) / np.maximum(np.abs(ref), np.maximum(floor, 1e-12))) < 1e-9
     pair = cam.astype(np.int64) * M + pose
     uniq, seg, cnt = np.unique(pair, return_inverse=True, return_counts=True)
     assert np.array_equal(sc.astype(np.int64) * M + sp, uniq) and np.array_equal(sl, cnt)

@@ -88,8 +88,10 @@ __global__ void k_f2f_down(int iters, float* out, double seed)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float f;
+            // the operand changes every iteration (integer add on the low word, other pipe), so nothing can be hoisted
+            a[i] = __longlong_as_double(__double_as_longlong(a[i]) + it);
             asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f) : "d"(a[i]));
-            acc[i] = __uint_as_float(__float_as_uint(acc[i]) ^ __float_as_uint(f));   // LOP3 on the other pipe keeps the result live
+            acc[i] = __uint_as_float(__float_as_uint(acc[i]) + __float_as_uint(f));   // integer add on the other pipe keeps the result live
         }
     }
     float s = 0;
@@ -108,8 +110,9 @@ __global__ void k_f2f_up(int iters, float* out, float seed)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             double d;
+            a[i] = __uint_as_float(__float_as_uint(a[i]) + it);
             asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(a[i]));
-            acc[i] ^= (unsigned long long)__double_as_longlong(d);
+            acc[i] += (unsigned long long)__double_as_longlong(d);
         }
     }
     unsigned long long s = 0;
