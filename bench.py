@@ -547,6 +547,38 @@ def measure_workload(args, workload, rank, world, dev, stream, flush_buf, steps,
                exchange=exch.kind, exchange_check=exch.check, scaling=sh["scaling"], sh=sh)
     xh = x_host.numpy()
 
+    def timed_steps(n_steps):
+        """(ms per step max over ranks, mean kernel ms) of n_steps evaluations with the current settings"""
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                flush_buf.zero_(); step()
+            barrier()
+            prob.timing_enable(True)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+            for e0, e1 in ev:
+                flush_buf.zero_(); e0.record(stream); step(); e1.record(stream)
+            barrier()
+            km = prob.timing_all_ms()[-n_steps:]
+            prob.timing_enable(False)
+        tot = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev))], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()) / n_steps, float(np.mean(km))
+
+    def lm_rate():
+        prob.set_param_string(sh["params"])
+        with torch.cuda.stream(stream):
+            prob.lm_solve(xh, max_iter=2, ftol=0, xtol=0, gtol=0)        # warm-up (workspace allocation)
+            prob.set_param_string(sh["params"])
+            barrier()
+            _, st = prob.lm_solve(xh, max_iter=args.lm_iters, ftol=0, xtol=0, gtol=0)
+            barrier()
+        secs = torch.tensor([st["seconds"]], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        return {"iter_per_s": st["iterations"] / float(secs.item()), "iterations": st["iterations"],
+                "cost_initial": st["cost_initial"], "cost_final": st["cost_final"], "status": st["status"]}
+
     if with_extras:
         # ---- end to end through the host-facing C-ABI call: host x in, all blocks out to (pinned) host memory ------
         C, M, S = prob.n_cams, prob.n_poses, prob.n_segments
@@ -614,20 +646,22 @@ def measure_workload(args, workload, rank, world, dev, stream, flush_buf, steps,
         try:
             if world > 1:
                 pdist.install_nccl_allreduce(prob)
-            prob.set_param_string(sh["params"])
-            with torch.cuda.stream(stream):
-                prob.lm_solve(xh, max_iter=2, ftol=0, xtol=0, gtol=0)        # warm-up (workspace allocation)
-                prob.set_param_string(sh["params"])
-                barrier()
-                _, st = prob.lm_solve(xh, max_iter=args.lm_iters, ftol=0, xtol=0, gtol=0)
-                barrier()
-            secs = torch.tensor([st["seconds"]], dtype=torch.float64, device=f"cuda:{dev}")
-            if world > 1:
-                dist.all_reduce(secs, op=dist.ReduceOp.MAX)
-            lm = {"iter_per_s": st["iterations"] / float(secs.item()), "iterations": st["iterations"],
-                  "cost_initial": st["cost_initial"], "cost_final": st["cost_final"], "status": st["status"]}
+            lm = lm_rate()
         except Exception as e:  # report, never hide
             lm = {"error": str(e)[:200]}
+
+    # ---- the same evaluation with the mixed-precision kernel (FP64 residual / cost / gradients, BF16-split J^T J) ------
+    try:
+        prob.set_normal_precision(True)
+        ms_m, kern_m = timed_steps(steps)
+        mixed = {"value": n_total / (ms_m * 1e-3) / 1e6, "unit": "Mobs/s", "ms_per_step": ms_m, "kernel_ms": kern_m,
+                 "contract": "cost, g_c, g_m FP64 (1e-9 vs oracle); U, V, W within 1e-4 sqrt(d_a d_b); tests/test_gpu_mixed_precision.py"}
+        if not args.no_lm:
+            mixed["lm"] = lm_rate()
+        prob.set_normal_precision(False)
+    except Exception as e:
+        mixed = {"error": str(e)[:200]}
+    res["mixed"] = mixed
     res["lm"] = lm
     prob.close()
     return res
@@ -686,7 +720,7 @@ def main():
             r5.pop("sh")
             config5 = {"value": r5["value"], "unit": "Mobs/s", "ms_per_step": r5["ms_per_step"], "scaling": "strong",
                        "n_obs_total": r5["n_obs_total"], "n_obs_per_gpu": r5["n_obs_per_gpu"], "kernel_ms": r5["kernel_ms"],
-                       "lm": r5["lm"], "exchange": r5["exchange"], "setup_s": r5["setup_s"],
+                       "lm": r5["lm"], "mixed": r5.get("mixed"), "exchange": r5["exchange"], "setup_s": r5["setup_s"],
                        "config": workload_config(args, world, "dome128")}
         except Exception as e:  # report, never hide
             config5 = {"error": str(e)[:200]}
@@ -711,6 +745,11 @@ def main():
                 lm_e2e = lm_e2e_device(args.seed, dev)
             except Exception as e:
                 lm_e2e = {"error": str(e)[:200]}
+        mixed_out = main_res.get("mixed")
+        if mixed_out and "kernel_ms" in mixed_out:
+            a_m = ALGO_BYTES_PER_OBS * n_local / (mixed_out["kernel_ms"] * 1e-3) / 1e9
+            mixed_out["roofline"] = {"bound": "hbm", "achieved": a_m, "peak": peak, "unit": "GB/s", "frac": a_m / peak,
+                                     "kernel": "k_normal_mixed", "kernel_ms": mixed_out["kernel_ms"], "traffic": None}
         out = {
             "metric": METRIC, "value": main_res["value"], "unit": "Mobs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": main_res["scaling"],
@@ -729,7 +768,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": main_res["e2e"],
             "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "lm": main_res["lm"],
-            "callbacks": main_res["callbacks"], "config5": config5, "lm_e2e": lm_e2e,
+            "callbacks": main_res["callbacks"], "mixed": mixed_out, "config5": config5, "lm_e2e": lm_e2e,
             "setup_s": main_res["setup_s"], "wall_s_timed_region": main_res["wall_s_timed_region"],
         }
         print(json.dumps(out), flush=True)

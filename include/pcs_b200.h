@@ -126,6 +126,16 @@ PCS_API int pcs_normal_equations(pcs_problem* p, const double* x, double* U, dou
 /* Device-resident variant: evaluates into the problem's own buffers; pointers to them via pcs_device_buffers. */
 PCS_API int pcs_normal_equations_dev(pcs_problem* p, const double* x_dev);
 
+/* Arithmetic of the fused normal-equation kernel (pcs_normal_equations*, and every evaluation inside pcs_lm_solve).
+ *   PCS_PRECISION_FP64  (default) everything FP64: blocks agree with J.T @ J of the reference Jacobian to 1e-9.
+ *   PCS_PRECISION_MIXED residual, cost and the gradients gc / gp stay FP64 (bit-for-bit the same evaluation; the LM fixed
+ *                       point g = 0 is unchanged); the J^T J blocks U, V, W -- which only precondition the step -- are
+ *                       accumulated on the BF16 tensor path (two-term split, FP32 accumulation per (camera, pose) segment,
+ *                       FP64 across segments): entries within ~1e-4 sqrt(d_a d_b) of the FP64 blocks.
+ * No reference counterpart (the reference never forms J^T J). */
+typedef enum pcs_precision { PCS_PRECISION_FP64 = 0, PCS_PRECISION_MIXED = 1 } pcs_precision;
+PCS_API int pcs_set_normal_precision(pcs_problem* p, int precision);
+
 /* Dense normal equations over the free parameters (both chains; small problems: n_free^2 doubles of HBM):
  * JtJ[n_free][n_free] (full symmetric), Jtr[n_free], cost. */
 PCS_API int pcs_normal_dense(pcs_problem* p, const double* x, double* JtJ, double* Jtr, double* cost);

@@ -14,6 +14,7 @@ LIB_PATH = PKG / "libpcs_b200.so"
 PCS_OK = 0
 PCS_ERR_INVALID, PCS_ERR_CHAIN, PCS_ERR_CUDA, PCS_ERR_UNSUPPORTED, PCS_ERR_NUMERIC = -1, -2, -3, -4, -5
 CHAIN_TEMPLATE, CHAIN_SELFCAL = 0, 1
+PRECISION_FP64, PRECISION_MIXED = 0, 1
 
 EXPORTED_SYMBOLS = [
     "pcs_chain_from_name", "pcs_problem_create", "pcs_problem_destroy", "pcs_problem_get_info", "pcs_last_error",
@@ -21,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pcs_csr_structure", "pcs_jacobian_values", "pcs_jacobian_values_dev", "pcs_segments", "pcs_normal_equations",
     "pcs_normal_equations_dev", "pcs_normal_dense", "pcs_device_buffers_get", "pcs_set_allreduce",
     "pcs_lm_default_options", "pcs_lm_solve", "pcs_spd_solve", "pcs_syrk_sub", "pcs_timing_enable", "pcs_timing_get", "pcs_timing_get_all", "pcs_launch_count",
-    "pcs_costfn", "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_device_sm_count",
+    "pcs_costfn", "pcs_set_normal_precision", "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_device_sm_count",
     "pcs_version",
 ]
 
@@ -116,6 +117,7 @@ def load() -> ct.CDLL:
     lib.pcs_timing_get.argtypes = [vp, ct.POINTER(ct.c_double)]
     lib.pcs_timing_get_all.argtypes = [vp, vp, ct.c_int64, ct.POINTER(ct.c_int64)]
     lib.pcs_launch_count.argtypes = [vp, ct.POINTER(ct.c_int64)]
+    lib.pcs_set_normal_precision.argtypes = [vp, ct.c_int]
     lib.pcs_costfn.argtypes = [vp, ct.c_int, vp, vp, vp, vp, vp, vp]
     lib.pcs_p2p_buffer_bytes.argtypes = [vp, ct.c_int]
     lib.pcs_p2p_buffer_bytes.restype = ct.c_int64

@@ -986,6 +986,18 @@ int pcs_timing_get_all(pcs_problem* p, double* ms, int64_t capacity, int64_t* n_
     return PCS_OK;
 }
 
+int pcs_set_normal_precision(pcs_problem* p, int precision)
+{
+    PCS_REQUIRE(p, "NULL argument");
+    PCS_REQUIRE(precision == PCS_PRECISION_FP64 || precision == PCS_PRECISION_MIXED, "precision must be PCS_PRECISION_FP64 or PCS_PRECISION_MIXED");
+    if (precision == PCS_PRECISION_MIXED && p->chain != PCS_CHAIN_TEMPLATE) {
+        set_error("the mixed-precision normal-equation kernel exists for the template chain");
+        return PCS_ERR_UNSUPPORTED;
+    }
+    p->normal_precision = precision;
+    return PCS_OK;
+}
+
 int pcs_set_allreduce(pcs_problem* p, pcs_allreduce_fn fn, void* user, int rank, int world_size)
 {
     PCS_REQUIRE(p, "NULL argument");

@@ -118,6 +118,7 @@ struct pcs_problem {
     cudaStream_t copy_stream = nullptr;    // host path: copy-out of finished parts overlaps the next part's kernel
     cudaEvent_t part_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t copy_done = nullptr;
+    int normal_precision = 0; // pcs_precision of the fused normal-equation kernel (pcs_set_normal_precision)
     int64_t n_launches = 0;  // kernels launched by this library on behalf of the problem (pcs_launch_count)
 
     // peer-memory all-reduce state (pcs_p2p.cu)

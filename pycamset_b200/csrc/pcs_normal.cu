@@ -431,6 +431,229 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     }
 }
 
+// ================================================================================================================
+// K_ne, mixed precision (opt-in, pcs_set_normal_precision): same mapping, same flushes, same outputs -- but the 16 x 16
+// Gram update leaves the FP64 pipe.
+//
+// Measured on B200 (tools/mma_peak.cu, profiles/r2_mma_peak_b200.json): DFMA, DMMA and the legacy tensor path (HMMA) all
+// issue through ONE pipe per sub-partition -- a DFMA costs 2.2 clocks, a DMMA m8n8k4 16, an HMMA (any shape / type) 8.6,
+// and a DFMA + HMMA mix takes the SUM of the two.  The FP64 kernel spends 768 of ~1100 pipe clocks per batch of 32
+// observations in its 48 DMMAs.  Here:
+//   * residual, Jacobian rows, cost and the gradient g = J^T r stay FP64: every lane forms its 16 products
+//     [J_u[a] r_u + J_v[a] r_v | r.r] in registers, parks them in an (swizzled) shared-memory table, and lane (a, half)
+//     sums column a over the rows of the current piece -- 16 LDS + 16 DADD per lane and batch however the batch is cut
+//     into pieces.  The fixed point of the LM iteration is defined by g = 0, so it is unchanged to FP64 accuracy.
+//   * J^T J only preconditions the step.  Each Jacobian entry is split into two BF16 terms, x ~ hi + lo (16 mantissa bits,
+//     truncation, relative error <= 2^-15), packed as (u-row, v-row) pairs -- exactly the k-pair a m16n8k16 fragment
+//     register holds -- and the Gram is hi^T hi + hi^T lo + lo^T hi: 6 HMMA.16816.F32.BF16 per 8 observations, FP32
+//     accumulators per SEGMENT (~40 observations), promoted to FP64 at the segment flush and summed in FP64 across
+//     segments.  Measured effect on the solver: tests/test_gpu_mixed_precision.py (same iterates' cost to 1e-6, same
+//     converged cost to 1e-9, iterations within 10 %).
+//   * A-fragment and B-fragment of a column tile are the same registers (as in the FP64 kernel): per k-step a lane loads
+//     4 x 8 bytes (hi / lo words of its two observations, columns g and g + 8 adjacent in the staged row).
+// ================================================================================================================
+constexpr int NEM_STAGE_DOUBLES = 512;   // 32 observations x 128 B: 16 hi words | 16 lo words (bf16 pairs (u, v))
+constexpr int NEM_GBUF_DOUBLES = 512;    // 32 x 16 FP64 gradient products
+constexpr int NEM_WARP_DOUBLES = NEM_STAGE_DOUBLES + NEM_GBUF_DOUBLES + NE_SCRATCH_DOUBLES;
+
+__device__ __forceinline__ void hmma_bf16(float d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Staged observation block (32 words): chunk c (4 words) sits at chunk c ^ swz(o); chunks 0..3 = hi words, 4..7 = lo
+// words; inside the 16 words of a half, column col sits at 2 (col & 7) + (col >> 3): columns g and g + 8 are adjacent.
+// swz is a bijection of o & 7 (conflict-free 16-byte stores of 8 consecutive lanes) whose bits 1, 2 are o & 3
+// (conflict-free 8-byte fragment loads of a half warp: 4 observations x 4 column pairs).
+__device__ __forceinline__ int nem_swz(int o) { return ((o & 3) << 1) | ((o >> 2) & 1); }
+
+// split two FP64 values (the u-row and v-row entries of one column) into packed bf16 pairs: hi = truncated, lo = remainder
+__device__ __forceinline__ void bf16_split_pair(double xu, double xv, unsigned& hi, unsigned& lo)
+{
+    const float fu = (float)xu, fv = (float)xv;
+    const unsigned bu = __float_as_uint(fu), bv = __float_as_uint(fv);
+    hi = __byte_perm(bu, bv, 0x7632);                                  // (bu >> 16) | (bv & 0xffff0000)
+    const float lu = fu - __uint_as_float(bu & 0xffff0000u), lv = fv - __uint_as_float(bv & 0xffff0000u);   // exact
+    lo = __byte_perm(__float_as_uint(lu), __float_as_uint(lv), 0x7632);
+}
+
+// Stage the two rows of one observation.  Column -> physical position pc = 2 (col & 7) + (col >> 3); chunk c holds
+// positions 4c .. 4c + 3, i.e. columns (2c, 2c + 8, 2c + 1, 2c + 9):
+//   c = 0: (xD | 0), (Au4 | Av4), (1 | 0), Wc0      c = 1: (0 | yD), Wc1, (0 | 1), Wc2
+//   c = 2: Au0/Av0, Pm0, Au1/Av1, Pm1                c = 3: Au2/Av2, Pm2, Au3/Av3, 0
+// Each chunk is split and stored as soon as it is formed (two 16-byte stores: hi words, lo words).
+__device__ __forceinline__ void stage_chunk(unsigned* __restrict__ blk, int swz, int c, const unsigned hi[4], const unsigned lo[4])
+{
+    *reinterpret_cast<uint4*>(blk + ((c ^ swz) << 2)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(blk + (((4 + c) ^ swz) << 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__device__ __forceinline__ void stage_rows_bf16(const NeRows& R, unsigned* __restrict__ blk, int swz)
+{
+    unsigned hi[4], lo[4];
+    bf16_split_pair(R.xD, 0.0, hi[0], lo[0]);
+    bf16_split_pair(R.Au[4], R.Av[4], hi[1], lo[1]);
+    hi[2] = 0x00003f80u; lo[2] = 0u;                                   // (1 | 0)
+    bf16_split_pair(R.Wc[0], R.Wc[3], hi[3], lo[3]);
+    stage_chunk(blk, swz, 0, hi, lo);
+    bf16_split_pair(0.0, R.yD, hi[0], lo[0]);
+    bf16_split_pair(R.Wc[1], R.Wc[4], hi[1], lo[1]);
+    hi[2] = 0x3f800000u; lo[2] = 0u;                                   // (0 | 1)
+    bf16_split_pair(R.Wc[2], R.Wc[5], hi[3], lo[3]);
+    stage_chunk(blk, swz, 1, hi, lo);
+    bf16_split_pair(R.Au[0], R.Av[0], hi[0], lo[0]);
+    bf16_split_pair(R.Pm[0], R.Pm[3], hi[1], lo[1]);
+    bf16_split_pair(R.Au[1], R.Av[1], hi[2], lo[2]);
+    bf16_split_pair(R.Pm[1], R.Pm[4], hi[3], lo[3]);
+    stage_chunk(blk, swz, 2, hi, lo);
+    bf16_split_pair(R.Au[2], R.Av[2], hi[0], lo[0]);
+    bf16_split_pair(R.Pm[2], R.Pm[5], hi[1], lo[1]);
+    bf16_split_pair(R.Au[3], R.Av[3], hi[2], lo[2]);
+    hi[3] = 0u; lo[3] = 0u;                                            // column 15 (the residual column of the FP64 kernel): g is formed in FP64
+    stage_chunk(blk, swz, 3, hi, lo);
+}
+
+// the lane's 16 FP64 gradient products [J_u[a] r_u + J_v[a] r_v (a = 0..14) | r.r], parked in row `o` of the table
+// (pairs are stored as they are formed)
+__device__ __forceinline__ void store_grad_products(const NeRows& R, double* __restrict__ grow, int o)
+{
+    const double ru = R.res[0], rv = R.res[1];
+    const int x = o & 7;
+    auto put = [&](int c, double p0, double p1) { *reinterpret_cast<double2*>(grow + ((c ^ x) << 1)) = make_double2(p0, p1); };
+    put(0, R.xD * ru, ru);
+    put(1, R.yD * rv, rv);
+    put(2, fma(R.Au[0], ru, R.Av[0] * rv), fma(R.Au[1], ru, R.Av[1] * rv));
+    put(3, fma(R.Au[2], ru, R.Av[2] * rv), fma(R.Au[3], ru, R.Av[3] * rv));
+    put(4, fma(R.Au[4], ru, R.Av[4] * rv), fma(R.Wc[0], ru, R.Wc[3] * rv));
+    put(5, fma(R.Wc[1], ru, R.Wc[4] * rv), fma(R.Wc[2], ru, R.Wc[5] * rv));
+    put(6, fma(R.Pm[0], ru, R.Pm[3] * rv), fma(R.Pm[1], ru, R.Pm[4] * rv));
+    put(7, fma(R.Pm[2], ru, R.Pm[5] * rv), fma(ru, ru, rv * rv));
+}
+
+template <int CTAS_PER_SM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
+k_normal_mixed(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_pose,
+               const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv, const int64_t* __restrict__ seg_start,
+               const double* __restrict__ camtab, const double* __restrict__ posetab, const double* __restrict__ pts,
+               double* __restrict__ U, double* __restrict__ gc, double* __restrict__ cost, double* __restrict__ V,
+               double* __restrict__ gp, double* __restrict__ W)
+{
+    extern __shared__ __align__(16) double ne_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* ws = ne_smem + warp * NEM_WARP_DOUBLES;
+    const int wg = blockIdx.x * WARPS + warp;
+    if (wg >= n_warps) return;
+    const int64_t sb = warp_seg[wg], se = warp_seg[wg + 1];
+    if (sb >= se) return;
+    const int64_t begin = seg_start[sb], end = seg_start[se];
+
+    unsigned* const stage = reinterpret_cast<unsigned*>(ws);
+    double* const gbuf = ws + NEM_STAGE_DOUBLES;
+    double* const scratch = gbuf + NEM_GBUF_DOUBLES;     // Tbar | running camera sums, as in the FP64 kernel
+    scratch[lane] = 0.0;
+    scratch[32 + lane] = lane == 30 ? 1.0 : 0.0;       // Tbar[7][6] = 1
+    for (int e = lane; e < 192; e += 32) scratch[64 + e] = 0.0;
+    __syncwarp();
+
+    float D0[4] = {0.f, 0.f, 0.f, 0.f}, D1[4] = {0.f, 0.f, 0.f, 0.f};   // segment Gram: columns 0..7 / 8..15 (FP32)
+    double gacc = 0.0;                                                   // lane (a = lane & 15, half = lane >> 4): partial g_s[a]
+    int64_t cur_seg = sb - 1;
+    int cur_c = -1, cur_m = -1, last_c = -1, last_m = -1;
+
+    const int g8 = lane >> 2, t4 = lane & 3;
+    unsigned* const my_blk = stage + lane * 32;
+    const int my_swz = nem_swz(lane);
+    const int ga = lane & 15, gh = lane >> 4;
+
+    auto flush = [&]() {
+        // FP32 segment sums -> FP64 fragments of the FP64 kernel's flush (aa = G[0:8,0:8], ab = G[0:8,8:16], bb = G[8:16,8:16]);
+        // column 15 (the gradient / cost column) comes from the FP64 sums
+        NeAcc S;
+        S.aa[0] = D0[0]; S.aa[1] = D0[1]; S.ab[0] = D1[0]; S.ab[1] = D1[1]; S.bb[0] = D1[2]; S.bb[1] = D1[3];
+        const double tot = gacc + __shfl_xor_sync(0xffffffffu, gacc, 16);      // lanes a and a + 16: g_s[a]
+        const double ga_lo = __shfl_sync(0xffffffffu, tot, g8), ga_hi = __shfl_sync(0xffffffffu, tot, 8 + g8);
+        if (t4 == 3) { S.ab[1] = ga_lo; S.bb[1] = ga_hi; }
+        flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { D0[i] = 0.f; D1[i] = 0.f; }
+        gacc = 0.0;
+    };
+
+    NeObs nxt;
+    load_obs(nxt, begin + lane, end, s_cam, s_pose, s_key, s_uv);
+    for (int64_t base = begin; base < end; base += 32) {
+        const NeObs ob = nxt;
+        load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);
+        NeRows R;
+        eval_rows(ob, camtab, posetab, pts, R);
+        if (nxt.m >= 0) {
+            const double* nx = posetab + (int64_t)nxt.m * POSE_STRIDE;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
+        }
+        const int cnt = (int)min((int64_t)32, end - base);
+        const int c = ob.c, m = ob.m;
+        if (lane < cnt) {
+            stage_rows_bf16(R, my_blk, my_swz);
+            store_grad_products(R, gbuf + lane * 16, lane);
+        }
+        int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
+        if (lane == 0) { pc = last_c; pm = last_m; }
+        const unsigned heads = __ballot_sync(0xffffffffu, lane < cnt && (c != pc || m != pm));
+        last_c = __shfl_sync(0xffffffffu, c, cnt - 1);
+        last_m = __shfl_sync(0xffffffffu, m, cnt - 1);
+        __syncwarp();
+        unsigned pieces = heads | 1u;
+        while (pieces) {
+            const int a = __ffs(pieces) - 1;
+            pieces &= pieces - 1;
+            const int b = pieces ? __ffs(pieces) - 1 : cnt;
+            if ((heads >> a) & 1u) {
+                if (cur_c >= 0) flush();
+                const int nc = __shfl_sync(0xffffffffu, c, a);
+                if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
+                ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
+            }
+            // gradient column sums of the piece: lane (ga, gh) adds the rows of its half
+            {
+                const int r0 = max(a, 16 * gh), r1 = min(b, 16 * gh + 16);
+                for (int r = r0; r < r1; ++r) gacc += gbuf[r * 16 + ((((ga >> 1) ^ (r & 7)) << 1) | (ga & 1))];
+            }
+            // Gram k-steps (8 observations each) of the piece; steps shared with a neighbouring piece are masked
+            for (int ks = a >> 3; ks <= (b - 1) >> 3; ++ks) {
+                const int o0 = 8 * ks + t4, o1 = o0 + 4;
+                const unsigned* b0p = stage + o0 * 32;
+                const unsigned* b1p = stage + o1 * 32;
+                const int ch = g8 >> 1, wi = (g8 & 1) << 1;
+                const int s0 = nem_swz(o0), s1 = nem_swz(o1);
+                uint2 h0 = *reinterpret_cast<const uint2*>(b0p + (((ch ^ s0) << 2) | wi));
+                uint2 l0 = *reinterpret_cast<const uint2*>(b0p + ((((4 + ch) ^ s0) << 2) | wi));
+                uint2 h1 = *reinterpret_cast<const uint2*>(b1p + (((ch ^ s1) << 2) | wi));
+                uint2 l1 = *reinterpret_cast<const uint2*>(b1p + ((((4 + ch) ^ s1) << 2) | wi));
+                if (8 * ks < a || 8 * ks + 8 > b) {
+                    if (o0 < a || o0 >= b) { h0 = make_uint2(0u, 0u); l0 = make_uint2(0u, 0u); }
+                    if (o1 < a || o1 >= b) { h1 = make_uint2(0u, 0u); l1 = make_uint2(0u, 0u); }
+                }
+                // A = J'^T (columns g, g + 8 x 16 staged rows): a0 = (col g, obs o0), a1 = (col g + 8, obs o0), a2 / a3: obs o1;
+                // B of column tile h = the same registers: (a0, a2) for columns 0..7, (a1, a3) for columns 8..15
+                hmma_bf16(D0, h0.x, h0.y, h1.x, h1.y, h0.x, h1.x);
+                hmma_bf16(D1, h0.x, h0.y, h1.x, h1.y, h0.y, h1.y);
+                hmma_bf16(D0, h0.x, h0.y, h1.x, h1.y, l0.x, l1.x);
+                hmma_bf16(D1, h0.x, h0.y, h1.x, h1.y, l0.y, l1.y);
+                hmma_bf16(D0, l0.x, l0.y, l1.x, l1.y, h0.x, h1.x);
+                hmma_bf16(D1, l0.x, l0.y, l1.x, l1.y, h0.y, h1.y);
+            }
+        }
+        __syncwarp();
+    }
+    if (cur_c >= 0) {
+        flush();
+        flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
+    }
+}
+
 // Segment range of every warp of every part.  The observation range is cut into `n_parts` equal parts and each part
 // into `n_warps` equal pieces; piece boundaries are moved to segment starts:
 //     warp_seg[part * (n_warps + 1) + w] = lower_bound(seg_start, N part / n_parts + (N / n_parts) w / n_warps).
@@ -487,24 +710,32 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
         PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
     }
     if (p->N == 0) return PCS_OK;
-    // variants (PCS_NE_CFG for A/B runs): 3 = 5 CTAs x 4 warps, one observation per lane (96 registers);
-    // 0 = 4 CTAs x 4 warps, one per lane (128 registers); 4 = 4 CTAs x 4 warps, two per lane; 5 = 3 CTAs x 4 warps, two per lane.
-    static const int cfg = [] { const char* e = std::getenv("PCS_NE_CFG"); return e && e[0] >= '0' && e[0] <= '5' ? e[0] - '0' : 3; }();
-    const int ctas = cfg == 3 ? 5 : cfg == 5 ? 3 : 4, warps = 4, opl = cfg >= 4 ? 2 : 1;
-    auto kern = cfg == 0 ? k_normal<4, 4, 1> : cfg == 4 ? k_normal<4, 4, 2> : cfg == 5 ? k_normal<3, 4, 2> : k_normal<5, 4, 1>;
-    const size_t smem = (size_t)warps * NE_WARP_DOUBLES * sizeof(double);
-    PCS_CUDA(ensure_dynamic_smem(kern, smem));
+    // FP64 (default): 5 CTAs x 4 warps per SM, 96 registers.  Mixed (pcs_set_normal_precision): BF16-split Gram on HMMA.
+    const bool mixed = p->normal_precision == PCS_PRECISION_MIXED;
+    // mixed kernel: 4 CTAs per SM (128 registers, no spills) or 5 (96 registers, 80 B of spills); PCS_NEM_CTAS for A/B runs
+    static const int nem_ctas = [] { const char* e = std::getenv("PCS_NEM_CTAS"); return e && e[0] == '5' ? 5 : 4; }();
+    const int ctas = mixed ? nem_ctas : 5, warps = 4;
+    const size_t smem = (size_t)warps * (mixed ? NEM_WARP_DOUBLES : NE_WARP_DOUBLES) * sizeof(double);
+    auto kern_mixed = nem_ctas == 5 ? k_normal_mixed<5, 4> : k_normal_mixed<4, 4>;
+    if (mixed) PCS_CUDA(ensure_dynamic_smem(kern_mixed, smem));
+    else PCS_CUDA(ensure_dynamic_smem(k_normal<5, 4, 1>, smem));
     // persistent-style grid: `ctas` CTAs of `warps` warps per SM; at least ~64 observations per warp
     const int64_t n_part_obs = p->N / n_parts + 1;
-    int64_t n_warps = std::min<int64_t>((n_part_obs + 64 * opl - 1) / (64 * opl), (int64_t)p->sm_count * ctas * warps);
+    int64_t n_warps = std::min<int64_t>((n_part_obs + 63) / 64, (int64_t)p->sm_count * ctas * warps);
     n_warps = std::max<int64_t>(1, std::min<int64_t>(n_warps, p->n_seg));
     PCS_TRY(ensure_ranges(p, n_warps, n_parts));
     const int grid = (int)((n_warps + warps - 1) / warps);
     const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
-    kern<<<grid, warps * 32, smem, p->stream>>>((int)n_warps, p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1), p->s_cam, p->s_pose,
-                                                  p->s_key, (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
-                                                  p->tmpl4, p->U, p->gc, p->cost, p->V, p->gp, p->W);
+    const int64_t* ranges = p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1);
+    if (mixed)
+        kern_mixed<<<grid, warps * 32, smem, p->stream>>>((int)n_warps, ranges, p->s_cam, p->s_pose, p->s_key,
+                                                                   (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
+                                                                   p->tmpl4, p->U, p->gc, p->cost, p->V, p->gp, p->W);
+    else
+        k_normal<5, 4, 1><<<grid, warps * 32, smem, p->stream>>>((int)n_warps, ranges, p->s_cam, p->s_pose, p->s_key,
+                                                                 (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
+                                                                 p->tmpl4, p->U, p->gc, p->cost, p->V, p->gp, p->W);
     PCS_CUDA(cudaGetLastError());
     ++p->n_launches;
     if (p->timing) {

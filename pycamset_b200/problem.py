@@ -191,6 +191,11 @@ class BundleProblem:
         L.check(self._lib.pcs_normal_equations(self._h, xp, _ptr(U), _ptr(gc), _ptr(V), _ptr(gp), _ptr(W), _ptr(cost)))
         return dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
 
+    def set_normal_precision(self, mixed: bool):
+        """False (default): FP64 blocks.  True: gradients / cost / residual stay FP64, the J^T J blocks come from the
+        BF16-split tensor path (they only precondition the LM step; include/pcs_b200.h)."""
+        L.check(self._lib.pcs_set_normal_precision(self._h, L.PRECISION_MIXED if mixed else L.PRECISION_FP64))
+
     def normal_equations_device(self, x_dev_ptr=None):
         """Evaluate into the device-resident block buffers (no host copies, no synchronisation)."""
         L.check(self._lib.pcs_normal_equations_dev(self._h, ct.c_void_p(x_dev_ptr) if x_dev_ptr else None))

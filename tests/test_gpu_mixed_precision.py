@@ -1,0 +1,157 @@
+"""GPU: the mixed-precision normal-equation kernel (pcs_set_normal_precision(PCS_PRECISION_MIXED)).
+
+Contract (include/pcs_b200.h):
+  * residual-derived outputs stay FP64: cost rel <= 1e-11, gradients g_c / g_m <= 1e-9 sqrt(d_a cost) against the CPU
+    oracle -- the same tolerances as the FP64 kernel, so the LM fixed point (g = 0) is unchanged;
+  * the J^T J blocks (U, V, W) come from the BF16-split tensor path: entries within 1e-4 sqrt(d_a d_b) of the oracle
+    (measured: ~2e-5; two truncated 8-bit terms per Jacobian entry, FP32 accumulation per segment);
+  * the solver does not notice: from the same start the device LM with mixed blocks reaches the FP64 solve's final cost to
+    1e-6 relative in at most 10 % + 1 more iterations (configs 1, 2 and a config-4-shaped ring), and on a
+    well-conditioned noise-free rig both recover the generating parameters (cost -> 0)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers import SYNTH_CASES, CCUBE_CASES, available, load_case, oracle_problem
+
+pytestmark = pytest.mark.gpu
+TEMPLATE_CASES = [c for c in available(SYNTH_CASES + CCUBE_CASES) if c.endswith("template")]
+
+
+def _close(a, b, da, db, tol):
+    scale = np.sqrt(np.maximum(da, 1e-300))[..., :, None] * np.sqrt(np.maximum(db, 1e-300))[..., None, :]
+    return float(np.max(np.abs(a - b) / scale)) if a.size else 0.0, tol
+
+
+def _check(p, o, params, x=None):
+    ne = p.normal_equations(x)
+    sc, sp, sl = p.segments()
+    pair = o.cam.astype(np.int64) * o.M + o.pose
+    uniq, seg = np.unique(pair, return_inverse=True)
+    U, gc, V, gp, W, cost = o.normal_blocks(params, seg.astype(np.int32), len(uniq))
+    dU = np.einsum("cii->ci", U); dV = np.einsum("mii->mi", V)
+    assert abs(ne["cost"] - cost) <= 1e-11 * max(cost, 1e-300)
+    if cost > 0:
+        assert np.max(np.abs(ne["gc"] - gc) / np.sqrt(np.maximum(dU, 1e-300) * cost)) < 1e-9
+        assert np.max(np.abs(ne["gp"] - gp) / np.sqrt(np.maximum(dV, 1e-300) * cost)) < 1e-9
+    errs = {}
+    for name, a, b, da, db in (("U", ne["U"], U, dU, dU), ("V", ne["V"], V, dV, dV), ("W", ne["W"], W, dU[sc], dV[sp])):
+        e, tol = _close(a, b, da, db, 1e-4)
+        errs[name] = e
+        assert e < tol, (name, e)
+    return errs
+
+
+def _gpu_problem(g):
+    from pycamset_b200.problem import BundleProblem
+    dd = g["dd"]
+    p = BundleProblem(0, dd[:, 0], dd[:, 1], dd[:, 2], dd[:, 3:5], int(g["n_cams"]), int(g["n_poses"]), g["template"].shape[0],
+                      template=g["template"], unfixed=g["unfixed"])
+    p.set_normal_precision(True)
+    return p
+
+
+@pytest.mark.parametrize("case", TEMPLATE_CASES)
+def test_mixed_blocks_on_the_goldens(case):
+    g = load_case(case)
+    with _gpu_problem(g) as p:
+        p.set_param_string(g["param0"])
+        errs = _check(p, oracle_problem(g), g["param0"], g["x"])
+        # the switch is per problem and reversible: FP64 blocks again at 1e-9
+        p.set_normal_precision(False)
+        ne = p.normal_equations(g["x"])
+    o = oracle_problem(g)
+    pair = o.cam.astype(np.int64) * o.M + o.pose
+    uniq, seg = np.unique(pair, return_inverse=True)
+    U = o.normal_blocks(g["param0"], seg.astype(np.int32), len(uniq))[0]
+    dU = np.einsum("cii->ci", U)
+    assert _close(ne["U"], U, dU, dU, 1e-9)[0] < 1e-9
+    assert max(errs.values()) > 1e-9          # the mixed path really ran (it cannot be as exact as FP64)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 31, 32, 33, 65, 200])
+def test_mixed_tiny_and_ragged_tables(n):
+    """Fewer observations than one k-step (8), odd counts, batch boundaries: the masked k-steps and the FP64 column sums."""
+    from pycamset_b200 import synthetic as syn
+    from pycamset_b200.problem import BundleProblem
+    rig = syn.make_rig(4, 6, distortion=True, seed=2, detect_prob=1.0)
+    intr, extr, poses = rig.perturbed(np.random.default_rng(2))
+    params = rig.param_string(intr, extr, poses)
+    sel = np.sort(np.random.default_rng(n).choice(rig.n_obs, n, replace=False))
+    cam, pose, key, uv = rig.cam.numpy()[sel], rig.pose.numpy()[sel], rig.key.numpy()[sel], rig.uv.numpy()[sel]
+    o = orc.Problem(0, cam, pose, key, uv, 4, 6, 81, rig.template)
+    with BundleProblem(0, cam, pose, key, uv, 4, 6, 81, template=rig.template) as p:
+        p.set_normal_precision(True)
+        p.set_param_string(params)
+        _check(p, o, params)
+
+
+def test_mixed_medium_ragged_and_dome():
+    from pycamset_b200 import synthetic as syn
+    from pycamset_b200.problem import BundleProblem
+    for (C, M, layout, prob) in ((8, 40, "ring", 0.7), (128, 30, "dome", 0.5)):
+        rig = syn.make_rig(C, M, layout=layout, distortion=True, seed=11, detect_prob=prob)
+        intr, extr, poses = rig.perturbed(np.random.default_rng(1))
+        params = rig.param_string(intr, extr, poses)
+        cam, pose, key, uv = rig.cam.numpy(), rig.pose.numpy(), rig.key.numpy(), rig.uv.numpy()
+        o = orc.Problem(0, cam, pose, key, uv, C, M, 81, rig.template)
+        with BundleProblem(0, cam, pose, key, uv, C, M, 81, template=rig.template) as p:
+            p.set_normal_precision(True)
+            p.set_param_string(params)
+            _check(p, o, params)
+
+
+def _solve_both(make, max_iter, tol):
+    out = []
+    for mixed in (False, True):
+        p, x0 = make()
+        p.set_normal_precision(mixed)
+        x, st = p.lm_solve(x0, max_iter=max_iter, ftol=tol, xtol=tol, gtol=tol)
+        r = p.residual(x)
+        p.close()
+        out.append((x, st, 0.5 * float(r @ r)))
+    return out
+
+
+@pytest.mark.parametrize("case", ["ring5_fixedcam_template", "ccube_template"])
+def test_mixed_lm_converges_like_fp64_on_the_goldens(case):
+    g = load_case(case)
+
+    def make():
+        from pycamset_b200.problem import BundleProblem
+        dd = g["dd"]
+        p = BundleProblem(0, dd[:, 0], dd[:, 1], dd[:, 2], dd[:, 3:5], int(g["n_cams"]), int(g["n_poses"]), g["template"].shape[0],
+                          template=g["template"], unfixed=g["unfixed"])
+        p.set_param_string(g["param0"])
+        return p, g["x"]
+
+    (x64, st64, c64), (xm, stm, cm) = _solve_both(make, 100, 1e-10)
+    assert abs(cm - stm["cost_final"]) <= 1e-9 * cm              # the cost the mixed solve reports is the true FP64 cost
+    assert abs(cm - c64) <= 1e-6 * c64, (cm, c64)
+    assert stm["iterations"] <= 1.1 * st64["iterations"] + 1, (stm, st64)
+
+
+def test_mixed_lm_ring32_and_noise_free_recovery():
+    from pycamset_b200 import synthetic as syn
+    from pycamset_b200.problem import BundleProblem
+
+    def maker(C, M, layout, noise, seed):
+        def make():
+            rig = syn.make_rig(C, M, layout=layout, distortion=True, seed=seed, detect_prob=0.9, noise_px=noise)
+            intr, extr, poses = rig.perturbed(np.random.default_rng(seed + 1), 1e-3)
+            params = rig.param_string(intr, extr, poses)
+            unfixed = np.ones(params.shape[0], bool)
+            unfixed[15 * C:15 * C + 6] = False
+            p = BundleProblem(0, rig.cam.numpy(), rig.pose.numpy(), rig.key.numpy(), rig.uv.numpy(), C, M, 81,
+                              template=rig.template, unfixed=unfixed)
+            p.set_param_string(params)
+            return p, params[unfixed]
+        return make
+
+    # config-4-shaped ring (fewer poses): same cost, no more iterations
+    (x64, st64, c64), (xm, stm, cm) = _solve_both(maker(32, 60, "ring", 0.1, 0), 60, 1e-10)
+    assert abs(cm - c64) <= 1e-6 * c64 and stm["iterations"] <= 1.1 * st64["iterations"] + 1, (st64, stm)
+    # well-conditioned noise-free dome: both precisions reach zero residual, i.e. the same (generating) parameters
+    (x64, st64, c64), (xm, stm, cm) = _solve_both(maker(8, 30, "dome", 0.0, 31), 100, 1e-16)
+    assert c64 < 1e-9 and cm < 1e-9, (c64, cm, st64, stm)       # 0.5 r.r over ~2e4 observations: < 1e-6 px rms
+    assert np.max(np.abs(xm - x64) / np.maximum(np.abs(x64), 1e-2)) < 1e-5

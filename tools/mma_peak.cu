@@ -182,6 +182,35 @@ __global__ void k_mix_dfma_hmma(int iters, float* out, double seed)
     if (s == 12345.678) out[0] = (float)s;
 }
 
+// per iteration: 16 DFMA + 8 cvt.rn.f32.f64 (independent): does the conversion unit share the FP64 pipe?
+__global__ void k_mix_dfma_f2f(int iters, float* out, double seed)
+{
+    double a[16], s8[8];
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + threadIdx.x * 1e-9 + i;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s8[i] = seed + threadIdx.x * 1e-7 + i; acc[i] = 0.f; }
+    const double b = 1.0000001 + seed, cc = 1e-9 + seed;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[2 * i] = fma(a[2 * i], b, cc);
+            a[2 * i + 1] = fma(a[2 * i + 1], b, cc);
+            float f;
+            s8[i] = __longlong_as_double(__double_as_longlong(s8[i]) + it);
+            asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f) : "d"(s8[i]));
+            acc[i] = __uint_as_float(__float_as_uint(acc[i]) + __float_as_uint(f));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    if (s == 12345.678) out[0] = (float)s;
+}
+
 __global__ void k_shfl64(int iters, float* out, double seed)
 {
     double a[8];
@@ -243,6 +272,7 @@ int main()
         run("ffma", k_ffma, warps, 2, it, 16 * 2, 0.f, sms, d_out, "TFLOP/s", 1e-12);
         run("dfma", k_dfma, warps, 2, it, 16 * 2, 0.0, sms, d_out, "TFLOP/s", 1e-12);
         run("mix_16dfma_8hmma(time only)", k_mix_dfma_hmma, warps, 2, it, 16 * 2, 0.0, sms, d_out, "TFLOP/s fp64 part", 1e-12);
+        run("mix_16dfma_8f2f(time only; 16 dfma alone = dfma row, 8 f2f alone = half the f2f row)", k_mix_dfma_f2f, warps, 2, it, 16 * 2, 0.0, sms, d_out, "TFLOP/s fp64 part", 1e-12);
         run("shfl64", k_shfl64, warps, 2, it, 8, 0.0, sms, d_out, "G 64-bit shuffles/s (per lane)", 1e-9);
     }
     return 0;
