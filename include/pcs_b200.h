@@ -113,7 +113,7 @@ PCS_API int pcs_jacobian_values_dev(pcs_problem* p, const double* x_dev, double*
  * (camera, pose).  W[s] couples seg_cam[s] with seg_pose[s]. */
 PCS_API int pcs_segments(pcs_problem* p, int32_t* seg_cam /*[S]*/, int32_t* seg_pose /*[S]*/, int64_t* seg_len /*[S]*/);
 
-/* Fused residual + Jacobian + J^T J / J^T r (chain 0).  No reference counterpart: scipy's LSMR consumes the
+/* Fused residual + Jacobian + J^T J / J^T r (both chains).  No reference counterpart: scipy's LSMR consumes the
  * CSR Jacobian instead (optimisation_handling.py:88-98); defined as the blocks of J.T @ J and J.T @ r of the
  * reference Jacobian with no parameter fixed:
  *   U[C][15][15], gc[C][15]  camera blocks (9 intrinsic + 6 extrinsic columns)
@@ -125,6 +125,15 @@ PCS_API int pcs_normal_equations(pcs_problem* p, const double* x, double* U, dou
                                  double* W, double* cost);
 /* Device-resident variant: evaluates into the problem's own buffers; pointers to them via pcs_device_buffers. */
 PCS_API int pcs_normal_equations_dev(pcs_problem* p, const double* x_dev);
+
+/* Self-calibration chain (projection + extrinsic3D + rigidTform3d + free_point, standard_bundle_handler.py:129-226;
+ * free_point: function_block_implementations.py:216-240): the blocks of J.T @ J / J.T @ r that involve the target points,
+ * as of the last pcs_normal_equations* call (U, V, W, gc, gp of this chain are the blocks above):
+ *   Pk[K][3][3], gk[K][3]     point blocks
+ *   Xck[C][K][15][3]          camera x point coupling (zero for pairs without observations)
+ *   Ymk[M][K][6][3]           pose x point coupling
+ * Any pointer may be NULL.  PCS_ERR_UNSUPPORTED when (45 C + 18 M) K > 2^27 (the dense tables are not allocated). */
+PCS_API int pcs_point_blocks(pcs_problem* p, double* Pk, double* gk, double* Xck, double* Ymk);
 
 /* Arithmetic of the fused normal-equation kernel (pcs_normal_equations*, and every evaluation inside pcs_lm_solve).
  *   PCS_PRECISION_FP64  (default) everything FP64: blocks agree with J.T @ J of the reference Jacobian to 1e-9.

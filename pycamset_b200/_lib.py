@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "pcs_chain_from_name", "pcs_problem_create", "pcs_problem_destroy", "pcs_problem_get_info", "pcs_last_error",
     "pcs_set_param_string", "pcs_set_free", "pcs_get_param_string", "pcs_residual", "pcs_residual_dev",
     "pcs_csr_structure", "pcs_jacobian_values", "pcs_jacobian_values_dev", "pcs_segments", "pcs_normal_equations",
-    "pcs_normal_equations_dev", "pcs_normal_dense", "pcs_device_buffers_get", "pcs_set_allreduce",
+    "pcs_normal_equations_dev", "pcs_point_blocks", "pcs_normal_dense", "pcs_device_buffers_get", "pcs_set_allreduce",
     "pcs_lm_default_options", "pcs_lm_solve", "pcs_spd_solve", "pcs_syrk_sub", "pcs_timing_enable", "pcs_timing_get", "pcs_timing_get_all", "pcs_launch_count",
     "pcs_costfn", "pcs_set_normal_precision", "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_device_sm_count",
     "pcs_version",
@@ -106,6 +106,7 @@ def load() -> ct.CDLL:
     lib.pcs_segments.argtypes = [vp, vp, vp, vp]
     lib.pcs_normal_equations.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pcs_normal_equations_dev.argtypes = [vp, vp]
+    lib.pcs_point_blocks.argtypes = [vp, vp, vp, vp, vp]
     lib.pcs_normal_dense.argtypes = [vp, vp, vp, vp, vp]
     lib.pcs_device_buffers_get.argtypes = [vp, ct.POINTER(DeviceBuffers)]
     lib.pcs_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, ct.c_int, ct.c_int]

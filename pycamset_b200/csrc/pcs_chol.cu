@@ -11,7 +11,8 @@
 //     diagonal tile itself -- A_kk minus the (lagged) rank-32 update with panel k-1 -- and factors it in one warp
 //     (row per lane, pivots broadcast by shuffles), so nobody waits for a "diagonal done" message; it then applies the
 //     lagged update to its own tile and solves it against L_kk^T.  Tiles right of the panel only get the lagged update.
-//   * After the last phase CTA 0 runs the back substitution  x = L^-T y  out of shared memory.
+//   * After the last phase CTA 0 runs the back substitution  x = L^-T y  out of shared memory; a row block of L that does
+//     not fit the buffer (n > ~600) streams through it in chunks, so n is bounded by the device memory, not by the SM.
 // Tiles are assigned round-robin per phase, panel tiles first (one per CTA while the grid is wide enough).
 // The kernel is launched cooperatively (co-residency is required by the barrier); loads of data written by other
 // CTAs bypass L1 (ld.global.cg).
@@ -39,6 +40,7 @@ struct CholProblem {
     int* info;
     int64_t n, ld;
     int nb;
+    int rb_cols;        // capacity (columns, multiple of 32) of the row-block buffer of the back substitution
     long long* trace;   // optional [nb + 1][8] globaltimer stamps of CTA 0 (tools/chol_trace.cu), else nullptr
 };
 
@@ -397,15 +399,38 @@ k_chol_solve(CholProblem P)
         double* nxt = ((nb - 1 - k) & 1) ? D : Pk;
         const int rows = (int)::min((long long)TB, (long long)(P.n - (int64_t)TB * k));
         const int ncol = k * TB;
-        // row block k of L into shared memory, RB[c][r] = L[32 k + r][c], and the next diagonal block: asynchronous
-        // 16-byte copies when the addresses allow it (even leading dimension, full block), guarded loads otherwise
+        // Row block k of L goes through shared memory, RB[c][r] = L[32 k + r][c0 + c], in chunks of at most rb_cols
+        // columns: asynchronous 16-byte copies when the addresses allow it (even leading dimension, full block), guarded
+        // loads otherwise.  The first chunk and the next diagonal block are in flight while warp 0 solves the triangle.
         const bool fast = (P.ld % 2 == 0) && rows == TB;
-        if (fast) {
-            for (int e = threadIdx.x; e < ncol * (TB / 2); e += CHOL_THREADS) {
-                const int c = e >> 4, r = (e & 15) * 2;
-                cp_async16(RB + c * RB_STRIDE + r, P.A + (int64_t)c * P.ld + (int64_t)TB * k + r);
+        auto fetch_chunk = [&](int c0, int nc, int first_thread) {
+            const int nthr = CHOL_THREADS - first_thread;
+            if (fast) {
+                for (int e = threadIdx.x - first_thread; e < nc * (TB / 2); e += nthr) {
+                    if (e < 0) break;
+                    const int c = e >> 4, r = (e & 15) * 2;
+                    cp_async16(RB + c * RB_STRIDE + r, P.A + (int64_t)(c0 + c) * P.ld + (int64_t)TB * k + r);
+                }
+            } else {
+                for (int e0 = threadIdx.x - first_thread; e0 < nc * TB; e0 += 8 * nthr) {
+                    if (e0 < 0) break;
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int e = e0 + u * nthr;
+                        const int c = e >> 5, r = e & 31;
+                        v[u] = (e < nc * TB && r < rows) ? __ldcg(P.A + (int64_t)(c0 + c) * P.ld + (int64_t)TB * k + r) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int e = e0 + u * nthr;
+                        if (e < nc * TB) RB[(e >> 5) * RB_STRIDE + (e & 31)] = v[u];
+                    }
+                }
             }
-        }
+        };
+        const int nc0 = ::min(ncol, P.rb_cols);
+        if (fast) fetch_chunk(0, nc0, 0);
         if (k > 0)
             for (int e = threadIdx.x; e < TB * (TB / 2); e += CHOL_THREADS) {
                 const int r = e >> 4, c = (e & 15) * 2;
@@ -426,31 +451,24 @@ k_chol_solve(CholProblem P)
             }
             yv[k * TB + lane] = yc;
         } else if (!fast) {
-            for (int e0 = threadIdx.x - 32; e0 < ncol * TB; e0 += 8 * (CHOL_THREADS - 32)) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e = e0 + u * (CHOL_THREADS - 32);
-                    const int c = e >> 5, r = e & 31;
-                    v[u] = (e < ncol * TB && r < rows) ? __ldcg(P.A + (int64_t)c * P.ld + (int64_t)TB * k + r) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e = e0 + u * (CHOL_THREADS - 32);
-                    if (e < ncol * TB) RB[(e >> 5) * RB_STRIDE + (e & 31)] = v[u];
-                }
-            }
+            fetch_chunk(0, nc0, 32);
         }
         cp_async_wait_all();
         __syncthreads();
-        if (threadIdx.x < ncol) {
-            double xk[TB];
+        double xk[TB];
 #pragma unroll
-            for (int r = 0; r < TB; r += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(yv + k * TB + r);
-                xk[r] = v.x; xk[r + 1] = v.y;
+        for (int r = 0; r < TB; r += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(yv + k * TB + r);
+            xk[r] = v.x; xk[r + 1] = v.y;
+        }
+        for (int c0 = 0; c0 < ncol; c0 += P.rb_cols) {
+            const int nc = ::min(ncol - c0, P.rb_cols);
+            if (c0 > 0) {                        // later chunks of a long row block: fetched by all threads
+                fetch_chunk(c0, nc, 0);
+                cp_async_wait_all();
+                __syncthreads();
             }
-            for (int c = threadIdx.x; c < ncol; c += CHOL_THREADS) {
+            for (int c = threadIdx.x; c < nc; c += CHOL_THREADS) {
                 const double* col = RB + c * RB_STRIDE;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -462,18 +480,28 @@ k_chol_solve(CholProblem P)
                     s2 = fma(l1.x, xk[r + 2], s2);
                     s3 = fma(l1.y, xk[r + 3], s3);
                 }
-                yv[c] -= (s0 + s1) + (s2 + s3);
+                yv[c0 + c] -= (s0 + s1) + (s2 + s3);
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
     for (int e = threadIdx.x; e < P.n; e += CHOL_THREADS) P.rhs[e] = yv[e];
     trace_stamp(P, nb, 1);
 }
 
-size_t chol_smem_bytes(int nb)
+size_t chol_smem_bytes(int nb, int rb_cols)
 {
-    return (size_t)(5 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)std::max(nb - 1, 0) * TB * RB_STRIDE) * sizeof(double);
+    return (size_t)(5 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)rb_cols * RB_STRIDE) * sizeof(double);
+}
+
+// capacity of the row-block buffer: the whole longest row block when it fits the opt-in shared memory, else what fits
+int chol_rb_cols(int nb, int max_optin_bytes)
+{
+    const int want = std::max(nb - 1, 0) * TB;
+    const long long fixed = (long long)(5 * TILE_DOUBLES + 3 * TB + nb * TB) * (long long)sizeof(double) + 1024;
+    const long long room = ((long long)max_optin_bytes - fixed) / (long long)(RB_STRIDE * sizeof(double));
+    const int cap = (int)std::max<long long>(0, room / TB * TB);
+    return std::min(want, cap);
 }
 
 }  // namespace
@@ -483,12 +511,13 @@ int chol_prepare(int device, int64_t n, double** Ldiag, unsigned long long** bar
 {
     *grid = 0;
     const int nb = (int)((n + TB - 1) / TB);
-    const size_t smem = chol_smem_bytes(nb);
     int max_optin = 0, sms = 0, coop = 0;
     PCS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     PCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     PCS_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    if (!coop || smem > (size_t)max_optin) return PCS_OK;
+    const int rb_cols = chol_rb_cols(nb, max_optin);
+    const size_t smem = chol_smem_bytes(nb, rb_cols);
+    if (!coop || smem > (size_t)max_optin || (nb > 1 && rb_cols < TB)) return PCS_OK;
     // monotone per (kernel, device): a later, smaller problem must not lower the opt-in of a live larger one
     PCS_CUDA(ensure_dynamic_smem(k_chol_solve, smem));
     int per_sm = 0;
@@ -511,10 +540,14 @@ int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t l
     P.trace = trace;
     P.A = A; P.rhs = rhs; P.Ldiag = Ldiag; P.bar = bar; P.info = info; P.n = n; P.ld = ld;
     P.nb = (int)((n + TB - 1) / TB);
+    int dev = 0, max_optin = 0;
+    PCS_CUDA(cudaGetDevice(&dev));
+    PCS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    P.rb_cols = std::max(chol_rb_cols(P.nb, max_optin), TB);
     P.bar_base = *bar_base;
     *bar_base += (unsigned long long)P.nb * (unsigned long long)grid;
     void* args[] = {&P};
-    PCS_CUDA(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_THREADS), args, chol_smem_bytes(P.nb), st));
+    PCS_CUDA(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_THREADS), args, chol_smem_bytes(P.nb, chol_rb_cols(P.nb, max_optin)), st));
     return PCS_OK;
 }
 

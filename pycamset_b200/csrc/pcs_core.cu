@@ -81,7 +81,8 @@ __device__ __forceinline__ double param_value(double* __restrict__ params, const
 __global__ void k_prepare_tables(int C, int M, int64_t n_tail, double* __restrict__ params, const double* __restrict__ x,
                                  const int32_t* __restrict__ free_map, double* __restrict__ camtab,
                                  double* __restrict__ posetab, double* __restrict__ dRtab, double* __restrict__ zero,
-                                 int64_t n_zero)
+                                 int64_t n_zero, int64_t n_seg, const int32_t* __restrict__ seg_cam,
+                                 const int32_t* __restrict__ seg_pose, double* __restrict__ segtab, double* __restrict__ pts4)
 {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i = t; i < n_zero; i += (int64_t)gridDim.x * blockDim.x) zero[i] = 0.0;
@@ -113,8 +114,33 @@ __global__ void k_prepare_tables(int C, int M, int64_t n_tail, double* __restric
         for (int k = 0; k < 9; ++k) o[POSE_JL + k] = Jl[k];
         o[21] = o[22] = o[23] = 0.0;
         if (dRtab) rodrigues_jac(r, dRtab + 27 * t);
-    } else if (x && t < (int64_t)C + M + n_tail) {
-        param_value(params, x, free_map, 15 * (int64_t)C + 6 * (int64_t)M + (t - C - M));
+    } else if (t < (int64_t)C + M + n_tail) {
+        // chain 1: the free points follow the pose block; they are also kept as 16-byte rows (pts4) for the kernels
+        const int64_t j = t - C - M;
+        const double v = param_value(params, x, free_map, 15 * (int64_t)C + 6 * (int64_t)M + j);
+        pts4[4 * (j / 3) + j % 3] = v;
+    } else if (segtab && t >= (int64_t)C + M + n_tail && t < (int64_t)C + M + n_tail + n_seg) {
+        // residual kernel: one combined transform per (camera, pose) segment, X_c = (R_c R_m) X_t + (R_c t_m + t_c),
+        // formed from the parameters themselves (not from the tables other threads of this launch are still writing)
+        const int64_t s = t - C - M - n_tail;
+        const int c = seg_cam[s], m = seg_pose[s];
+        double ec[6], em[6], Rc[9], Rm[9];
+        for (int k = 0; k < 6; ++k) {
+            const int64_t ic = 9 * (int64_t)C + 6 * (int64_t)c + k, im = 15 * (int64_t)C + 6 * (int64_t)m + k;
+            const int32_t fc = x ? free_map[ic] : -1, fm = x ? free_map[im] : -1;
+            ec[k] = fc >= 0 ? x[fc] : params[ic];
+            em[k] = fm >= 0 ? x[fm] : params[im];
+        }
+        rodrigues(ec, Rc);
+        rodrigues(em, Rm);
+        double* o = segtab + s * SEG_STRIDE;
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b)
+                o[SEG_R + 3 * a + b] = fma(Rc[3 * a], Rm[b], fma(Rc[3 * a + 1], Rm[3 + b], Rc[3 * a + 2] * Rm[6 + b]));
+            o[SEG_T + a] = fma(Rc[3 * a], em[3], fma(Rc[3 * a + 1], em[4], fma(Rc[3 * a + 2], em[5], ec[3 + a])));
+        }
+        o[SEG_CAM] = __hiloint2double(0, c);
+        o[SEG_CAM + 1] = 0.0;
     }
 }
 
@@ -130,14 +156,16 @@ int launch_scatter_x(pcs_problem* p, const double* x_dev)
 
 // with_dR: also refresh the OpenCV dR/dr tables [C + M][27] the explicit-Jacobian / dense paths read.
 // x_dev / zero: see k_prepare_tables (one launch instead of scatter + tables + memset).
-int launch_prepare(pcs_problem* p, bool with_dR, const double* x_dev, double* zero, int64_t n_zero)
+int launch_prepare(pcs_problem* p, bool with_dR, const double* x_dev, double* zero, int64_t n_zero, bool with_seg)
 {
     if (with_dR && !p->dRtab) PCS_TRY(dev_alloc(&p->dRtab, 27 * ((int64_t)p->C + p->M)));
-    const int64_t n_tail = x_dev ? p->L - 15 * (int64_t)p->C - 6 * (int64_t)p->M : 0;
-    const int64_t threads = (int64_t)p->C + p->M + n_tail;
+    if (with_seg && !p->segtab) PCS_TRY(dev_alloc(&p->segtab, SEG_STRIDE * p->n_seg));
+    const int64_t n_tail = p->L - 15 * (int64_t)p->C - 6 * (int64_t)p->M;   // chain 1: 3 K point coordinates, chain 0: none
+    const int64_t threads = (int64_t)p->C + p->M + n_tail + (with_seg ? p->n_seg : 0);
     const int grid = (int)std::max<int64_t>(grid_for(threads, 128), std::min<int64_t>(grid_for(n_zero, 128), 2 * p->sm_count));
     k_prepare_tables<<<grid, 128, 0, p->stream>>>(p->C, p->M, n_tail, p->params, x_dev, p->free_map, p->camtab, p->posetab,
-                                                  with_dR ? p->dRtab : nullptr, zero, zero ? n_zero : 0);
+                                                  with_dR ? p->dRtab : nullptr, zero, zero ? n_zero : 0, p->n_seg, p->seg_cam,
+                                                  p->seg_pose, with_seg ? p->segtab : nullptr, p->tmpl4);
     ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;
@@ -151,27 +179,62 @@ static inline const double* points_ptr(const pcs_problem* p)
 // ------------------------------------------------------------------------------------------------
 // K_res: residual, one thread per observation, dd row order.  44 algorithmic bytes / observation.
 // ------------------------------------------------------------------------------------------------
+// Rows of the per-segment table and the camera table are fetched with 16-byte loads; the observation stream (segment id,
+// key, (u, v)) is read once and bypasses L1 allocation.  Per lane: 12 + 10 + 3..4 doubles of table rows instead of the
+// 34 + 3 of a separate pose and camera transform -- the kernel is bound by the bytes every lane has to RECEIVE through
+// the L1 data pipe (128 B / clock / SM), not by HBM, so fewer row bytes per observation is what makes it faster.
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p)
+{
+    int v;
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p)
+{
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+template <bool PTS4>
 __global__ void __launch_bounds__(256)
-k_residual(int64_t N, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose,
-           const int32_t* __restrict__ key, const double2* __restrict__ uv, const double* __restrict__ camtab,
-           const double* __restrict__ posetab, const double* __restrict__ pts, double2* __restrict__ r_out)
+k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __restrict__ key, const double2* __restrict__ uv,
+           const double* __restrict__ segtab, const double* __restrict__ camtab, const double* __restrict__ pts,
+           double2* __restrict__ r_out)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const int c = cam[i], m = pose[i], k = key[i];
-    const double2 o = uv[i];
-    const double* pt = pts + 3 * (int64_t)k;
-    const double Xt[3] = {pt[0], pt[1], pt[2]};
-    double res[2];
-    eval_residual(camtab + (int64_t)c * CAM_STRIDE, posetab + (int64_t)m * POSE_STRIDE, Xt, o.x, o.y, res);
-    r_out[i] = make_double2(res[0], res[1]);
+    const int s = ld_stream_i32(obs_seg + i), k = ld_stream_i32(key + i);
+    const double2 o = ld_stream_f64x2(uv + i);
+    double T[SEG_STRIDE], q[10], Xt[4];
+    {
+        const double2* row = reinterpret_cast<const double2*>(segtab + (int64_t)s * SEG_STRIDE);
+#pragma unroll
+        for (int j = 0; j < SEG_STRIDE / 2; ++j) { const double2 v = row[j]; T[2 * j] = v.x; T[2 * j + 1] = v.y; }
+        if (PTS4) {   // template chain: rows padded to 4 doubles
+            const double2* x2 = reinterpret_cast<const double2*>(pts + 4 * (int64_t)k);
+            const double2 a = x2[0], b = x2[1];
+            Xt[0] = a.x; Xt[1] = a.y; Xt[2] = b.x;
+        } else {
+            const double* pt = pts + 3 * (int64_t)k;
+            Xt[0] = pt[0]; Xt[1] = pt[1]; Xt[2] = pt[2];
+        }
+        const int c = __double2loint(T[SEG_CAM]);
+        const double2* qr = reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_STRIDE + CAM_Q);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { const double2 v = qr[j]; q[2 * j] = v.x; q[2 * j + 1] = v.y; }
+    }
+    double Xc[3];
+    transform(T + SEG_R, T + SEG_T, Xt, Xc);
+    const Proj p = project(q, Xc);
+    r_out[i] = make_double2(p.u - o.x, p.v - o.y);
 }
 
 int launch_residual(pcs_problem* p, double* r_dev)
 {
     if (p->N == 0) return PCS_OK;
-    k_residual<<<grid_for(p->N, 256), 256, 0, p->stream>>>(p->N, p->cam, p->pose, p->key, (const double2*)p->uv,
-                                                          p->camtab, p->posetab, points_ptr(p), (double2*)r_dev);
+    k_residual<true><<<grid_for(p->N, 256), 256, 0, p->stream>>>(p->N, p->obs_seg, p->key, (const double2*)p->uv, p->segtab,
+                                                                p->camtab, p->tmpl4, (double2*)r_dev);
     ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;
@@ -362,6 +425,75 @@ k_normal_dense(int64_t N, int C, int M, int64_t n_free, const int32_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Self-calibration chain (projection + extrinsic3D + rigidTform3d + free_point, standard_bundle_handler.py:129-226):
+// the blocks that involve the target points.  The camera / pose blocks U, V, W, g_c, g_m, r.r of this chain are the
+// template chain's with X_t = point[k] and come from the fused kernel (pcs_normal.cu); this kernel adds, per observation
+// (c, m, k) with B_k = Pm R_c R_m (2 x 3, function_block_implementations.py:226-240: d X_t / d point = I):
+//     Pk[k]    += B_k^T B_k          (3 x 3)       gk[k] += B_k^T r
+//     Xck[c,k] += [A | B_c]^T B_k    (15 x 3)      Ymk[m,k] += B_m^T B_k   (6 x 3)
+// Rotation columns are in the reference's rvec parametrisation (tangent rows times the left Jacobian), like the blocks the
+// fused kernel writes.  One lane per observation, FP64 reductions into the dense (camera, key) / (pose, key) tables:
+// 75 reductions per observation -- this chain's problems are small (N = 4884 at the reference's fixture).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_normal_points(int64_t N, int K, const int32_t* __restrict__ cam, const int32_t* __restrict__ pose, const int32_t* __restrict__ key,
+                const double2* __restrict__ uv, const double* __restrict__ camtab, const double* __restrict__ posetab,
+                const double* __restrict__ pts4, double* __restrict__ Pk, double* __restrict__ gk, double* __restrict__ Xck,
+                double* __restrict__ Ymk)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t c = cam[i], m = pose[i], k = key[i];
+    const double2 o = uv[i];
+    const double* ct = camtab + c * CAM_STRIDE;
+    const double* ptab = posetab + m * POSE_STRIDE;
+    const double Xt[3] = {pts4[4 * k], pts4[4 * k + 1], pts4[4 * k + 2]};
+    double res[2], Bc[6], Bm[6];
+    ObsJac J;
+    eval_obs(ct, ptab, Xt, o.x, o.y, res, J);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            Bc[3 * r + a] = J.Wc[3 * r] * ct[CAM_JL + a] + J.Wc[3 * r + 1] * ct[CAM_JL + 3 + a] + J.Wc[3 * r + 2] * ct[CAM_JL + 6 + a];
+            Bm[3 * r + a] = J.Wm[3 * r] * ptab[POSE_JL + a] + J.Wm[3 * r + 1] * ptab[POSE_JL + 3 + a] + J.Wm[3 * r + 2] * ptab[POSE_JL + 6 + a];
+        }
+    double ju[24], jv[24];
+    expand_rows<24>(J, Bc, Bm, ptab, ju, jv);
+    double* P = Pk + k * 9;
+    double* X = Xck + (c * K + k) * 45;
+    double* Y = Ymk + (m * K + k) * 18;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double bu = ju[21 + a], bv = jv[21 + a];
+        atomicAdd(gk + 3 * k + a, fma(bu, res[0], bv * res[1]));
+#pragma unroll
+        for (int b = 0; b < 3; ++b) atomicAdd(P + 3 * a + b, fma(bu, ju[21 + b], bv * jv[21 + b]));
+#pragma unroll
+        for (int r = 0; r < 15; ++r) {
+            const double v = fma(ju[r], bu, jv[r] * bv);
+            if (v != 0.0) atomicAdd(X + 3 * r + a, v);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) atomicAdd(Y + 3 * r + a, fma(ju[15 + r], bu, jv[15 + r] * bv));
+    }
+}
+
+int launch_point_blocks(pcs_problem* p)
+{
+    if (p->chain != PCS_CHAIN_SELFCAL || !p->Pk) {
+        set_error("point blocks exist for the self-calibration chain (and need (45 C + 18 M) K <= 2^27)");
+        return PCS_ERR_UNSUPPORTED;
+    }
+    if (p->N == 0) return PCS_OK;
+    k_normal_points<<<grid_for(p->N, 128), 128, 0, p->stream>>>(p->N, p->K, p->cam, p->pose, p->key, (const double2*)p->uv, p->camtab,
+                                                              p->posetab, p->tmpl4, p->Pk, p->gk, p->Xck, p->Ymk);
+    ++p->n_launches;
+    PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // problem build kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void k_validate_and_count(int64_t N, int C, int M, int K, int P, const int32_t* __restrict__ cam,
@@ -402,7 +534,7 @@ __global__ void k_segment_fill(int64_t N, int M, const uint64_t* __restrict__ ke
                                const int32_t* __restrict__ key_in, const double2* __restrict__ uv_in,
                                const int32_t* __restrict__ seg_scan, int32_t* __restrict__ s_cam, int32_t* __restrict__ s_pose,
                                int32_t* __restrict__ s_key, double2* __restrict__ s_uv, int32_t* __restrict__ seg_cam,
-                               int32_t* __restrict__ seg_pose, int64_t* __restrict__ seg_start)
+                               int32_t* __restrict__ seg_pose, int64_t* __restrict__ seg_start, int32_t* __restrict__ obs_seg)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -413,6 +545,7 @@ __global__ void k_segment_fill(int64_t N, int M, const uint64_t* __restrict__ ke
     s_pose[i] = m;
     s_key[i] = key_in[src];
     s_uv[i] = uv_in[src];
+    obs_seg[src] = seg;
     if (i == 0 || keys[i] != keys[i - 1]) {
         seg_cam[seg] = c;
         seg_pose[seg] = m;
@@ -461,7 +594,7 @@ int pcs_problem_destroy(pcs_problem* p)
     dev_free(p->free_map); dev_free(p->free_idx); dev_free(p->cam_mask); dev_free(p->pose_mask); dev_free(p->key_mask);
     dev_free(p->row_prefix); dev_free(p->params); dev_free(p->x); dev_free(p->camtab); dev_free(p->posetab);
     dev_free(p->resid); dev_free(p->jvals); dev_free(p->seg_cam); dev_free(p->seg_pose); dev_free(p->seg_start);
-    dev_free(p->s_key); dev_free(p->s_cam); dev_free(p->s_pose); dev_free(p->s_uv); dev_free(p->ne); dev_free(p->dense); dev_free(p->warp_seg[0]); dev_free(p->warp_seg[1]); dev_free(p->dRtab);
+    dev_free(p->s_key); dev_free(p->s_cam); dev_free(p->s_pose); dev_free(p->s_uv); dev_free(p->obs_seg); dev_free(p->segtab); dev_free(p->ne); dev_free(p->dense); dev_free(p->warp_seg[0]); dev_free(p->warp_seg[1]); dev_free(p->dRtab);
     if (p->h_pin) cudaFreeHost(p->h_pin);
     for (cudaEvent_t e : p->ev_a) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_b) cudaEventDestroy(e);
@@ -502,6 +635,9 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
         PCS_TRY(dev_alloc(&p->tmpl4, 4 * (int64_t)p->K));
         PCS_CUDA(cudaMemsetAsync(p->tmpl4, 0, (size_t)p->K * 32, st));
         PCS_CUDA(cudaMemcpy2DAsync(p->tmpl4, 32, d->template_xyz, 24, 24, (size_t)p->K, cudaMemcpyHostToDevice, st));
+    } else {
+        PCS_TRY(dev_alloc(&p->tmpl4, 4 * (int64_t)p->K));
+        PCS_CUDA(cudaMemsetAsync(p->tmpl4, 0, (size_t)p->K * 32, st));
     }
 
     // --- free map, masks, free index list (host, O(L)) ---------------------------------------
@@ -598,7 +734,7 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
 
     // --- (camera, pose)-sorted layout -------------------------------------------------------------
     BUILD_TRY(dev_alloc(&p->s_key, N)); BUILD_TRY(dev_alloc(&p->s_cam, N)); BUILD_TRY(dev_alloc(&p->s_pose, N));
-    BUILD_TRY(dev_alloc(&p->s_uv, 2 * N)); BUILD_TRY(dev_alloc(&seg_scan, N));
+    BUILD_TRY(dev_alloc(&p->s_uv, 2 * N)); BUILD_TRY(dev_alloc(&seg_scan, N)); BUILD_TRY(dev_alloc(&p->obs_seg, N));
     int64_t n_seg = 0;
     if (N > 0) {
         need = tmp_bytes;
@@ -619,7 +755,7 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     if (N > 0) {
         k_segment_fill<<<grid_for(N, 256), 256, 0, st>>>(N, p->M, keys_b, idx_b, p->key, (const double2*)p->uv, seg_scan, p->s_cam,
                                                          p->s_pose, p->s_key, (double2*)p->s_uv, p->seg_cam, p->seg_pose,
-                                                         p->seg_start);
+                                                         p->seg_start, p->obs_seg);
         BUILD_CUDA(cudaGetLastError());
     } else {
         BUILD_CUDA(cudaMemsetAsync(p->seg_start, 0, 8, st));
@@ -628,9 +764,18 @@ static int build_problem(pcs_problem* p, const pcs_problem_desc* d)
     // --- normal-equation outputs: [U | gc | cost | pad | V | gp | W] -------------------------------------
     const int64_t nU = (int64_t)p->C * 225, ngc = (int64_t)p->C * 15, nV = (int64_t)p->M * 36, ngp = (int64_t)p->M * 6;
     const int64_t head = (nU + ngc + 1 + 1) / 2 * 2;
-    p->ne_doubles = head + nV + ngp + n_seg * 90;
+    // chain 1: point blocks and the dense camera x point / pose x point coupling tables sit between gp and W (all of
+    // them are accumulated with reductions and cleared by the prepare launch); skipped when they would exceed 2^27 doubles
+    int64_t nP = 0, ngk = 0, nX = 0, nY = 0;
+    if (p->chain == PCS_CHAIN_SELFCAL && ((int64_t)p->C * 45 + (int64_t)p->M * 18) * p->K <= ((int64_t)1 << 27)) {
+        nP = ((int64_t)p->K * 9 + 1) / 2 * 2; ngk = ((int64_t)p->K * 3 + 1) / 2 * 2; nX = (int64_t)p->C * p->K * 45 / 2 * 2 + 2; nY = (int64_t)p->M * p->K * 18;
+    }
+    p->ne_doubles = head + nV + ngp + nP + ngk + nX + nY + n_seg * 90;
     BUILD_TRY(dev_alloc(&p->ne, p->ne_doubles));
-    p->U = p->ne; p->gc = p->U + nU; p->cost = p->gc + ngc; p->V = p->ne + head; p->gp = p->V + nV; p->W = p->gp + ngp;
+    p->U = p->ne; p->gc = p->U + nU; p->cost = p->gc + ngc; p->V = p->ne + head; p->gp = p->V + nV;
+    double* q = p->gp + ngp;
+    if (nP) { p->Pk = q; p->gk = p->Pk + nP; p->Xck = p->gk + ngk; p->Ymk = p->Xck + nX; q = p->Ymk + nY; }
+    p->W = q;
 
     BUILD_CUDA(cudaStreamSynchronize(st));
     cleanup();
@@ -722,8 +867,8 @@ int pcs_residual_dev(pcs_problem* p, const double* x_dev, double* r_dev)
 {
     PCS_REQUIRE(p && r_dev, "NULL argument");
     PCS_CUDA(cudaSetDevice(p->device));
-    if (x_dev) PCS_TRY(launch_scatter_x(p, x_dev));
-    PCS_TRY(launch_prepare(p));
+    // two launches per call: [x scatter + camera / pose tables + per-segment transforms] and the residual kernel
+    PCS_TRY(launch_prepare(p, false, x_dev, nullptr, 0, true));
     return launch_residual(p, r_dev);
 }
 
@@ -732,8 +877,14 @@ int pcs_residual(pcs_problem* p, const double* x, double* r_out)
     PCS_REQUIRE(p && r_out, "NULL argument");
     PCS_CUDA(cudaSetDevice(p->device));
     if (!p->resid) PCS_TRY(dev_alloc(&p->resid, 2 * p->N));
-    PCS_TRY(upload_x(p, x));
-    PCS_TRY(launch_prepare(p));
+    const double* x_dev = nullptr;
+    if (x && p->n_free > 0) {
+        PCS_TRY(ensure_pinned(p, p->n_free));
+        std::memcpy(p->h_pin, x, (size_t)p->n_free * 8);
+        PCS_CUDA(cudaMemcpyAsync(p->x, p->h_pin, (size_t)p->n_free * 8, cudaMemcpyHostToDevice, p->stream));
+        x_dev = p->x;
+    }
+    PCS_TRY(launch_prepare(p, false, x_dev, nullptr, 0, true));
     PCS_TRY(launch_residual(p, p->resid));
     if (p->N) PCS_CUDA(cudaMemcpyAsync(r_out, p->resid, (size_t)p->N * 16, cudaMemcpyDeviceToHost, p->stream));
     PCS_CUDA(cudaStreamSynchronize(p->stream));
@@ -813,27 +964,48 @@ int pcs_segments(pcs_problem* p, int32_t* seg_cam, int32_t* seg_pose, int64_t* s
     return PCS_OK;
 }
 
+static int require_block_path(const pcs_problem* p)
+{
+    if (p->chain == PCS_CHAIN_SELFCAL && !p->Pk) {
+        set_error("block normal equations of the self-calibration chain keep dense (camera, key) / (pose, key) tables and need "
+                  "(45 C + 18 M) K <= 2^27; use pcs_normal_dense for this problem");
+        return PCS_ERR_UNSUPPORTED;
+    }
+    return PCS_OK;
+}
+
 int pcs_normal_equations_dev(pcs_problem* p, const double* x_dev)
 {
     PCS_REQUIRE(p, "NULL argument");
-    if (p->chain != PCS_CHAIN_TEMPLATE) {
-        set_error("block normal equations are implemented for the template chain; use pcs_normal_dense for the self-calibration chain");
-        return PCS_ERR_UNSUPPORTED;
-    }
+    PCS_TRY(require_block_path(p));
     PCS_CUDA(cudaSetDevice(p->device));
-    // one launch: x -> parameter string, camera / pose tables, cleared reduction targets [U | gc | cost | pad | V | gp]
-    PCS_TRY(launch_prepare(p, false, x_dev, p->ne, (p->V - p->ne) + (int64_t)p->M * 42));
-    return launch_normal_blocks(p, true);
+    // one launch: x -> parameter string, camera / pose tables, cleared reduction targets [U | gc | cost | pad | V | gp (| point blocks)]
+    PCS_TRY(launch_prepare(p, false, x_dev, p->ne, ne_zero_doubles(p)));
+    PCS_TRY(launch_normal_blocks(p, true));
+    if (p->chain == PCS_CHAIN_SELFCAL) PCS_TRY(launch_point_blocks(p));
+    return PCS_OK;
+}
+
+int pcs_point_blocks(pcs_problem* p, double* Pk, double* gk, double* Xck, double* Ymk)
+{
+    PCS_REQUIRE(p, "NULL argument");
+    if (p->chain != PCS_CHAIN_SELFCAL) { set_error("point blocks exist for the self-calibration chain"); return PCS_ERR_UNSUPPORTED; }
+    PCS_TRY(require_block_path(p));
+    PCS_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    if (Pk) PCS_CUDA(cudaMemcpyAsync(Pk, p->Pk, (size_t)p->K * 9 * 8, cudaMemcpyDeviceToHost, st));
+    if (gk) PCS_CUDA(cudaMemcpyAsync(gk, p->gk, (size_t)p->K * 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (Xck) PCS_CUDA(cudaMemcpyAsync(Xck, p->Xck, (size_t)p->C * p->K * 45 * 8, cudaMemcpyDeviceToHost, st));
+    if (Ymk) PCS_CUDA(cudaMemcpyAsync(Ymk, p->Ymk, (size_t)p->M * p->K * 18 * 8, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(cudaStreamSynchronize(st));
+    return PCS_OK;
 }
 
 int pcs_normal_equations(pcs_problem* p, const double* x, double* U, double* gc, double* V, double* gp, double* W,
                          double* cost)
 {
     PCS_REQUIRE(p, "NULL argument");
-    if (p->chain != PCS_CHAIN_TEMPLATE) {
-        set_error("block normal equations are implemented for the template chain; use pcs_normal_dense for the self-calibration chain");
-        return PCS_ERR_UNSUPPORTED;
-    }
+    PCS_TRY(require_block_path(p));
     PCS_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = p->stream;
     // host x -> device (pinned staging), then one launch: scatter + tables + cleared reduction targets
@@ -844,7 +1016,7 @@ int pcs_normal_equations(pcs_problem* p, const double* x, double* U, double* gc,
         PCS_CUDA(cudaMemcpyAsync(p->x, p->h_pin, (size_t)p->n_free * 8, cudaMemcpyHostToDevice, st));
         x_dev = p->x;
     }
-    PCS_TRY(launch_prepare(p, false, x_dev, p->ne, (p->V - p->ne) + (int64_t)p->M * 42));
+    PCS_TRY(launch_prepare(p, false, x_dev, p->ne, ne_zero_doubles(p)));
     // W is by far the largest output (720 B per segment): the evaluation runs in parts and the copy-out of a finished
     // part's segments proceeds on a second stream while the next part is evaluated
     const int n_parts = (W && p->n_seg >= 4096) ? 4 : 1;
@@ -864,6 +1036,7 @@ int pcs_normal_equations(pcs_problem* p, const double* x, double* U, double* gc,
             }
         }
     }
+    if (p->chain == PCS_CHAIN_SELFCAL) PCS_TRY(launch_point_blocks(p));   // left on the device: pcs_point_blocks copies them out
     if (U) PCS_CUDA(cudaMemcpyAsync(U, p->U, (size_t)p->C * 225 * 8, cudaMemcpyDeviceToHost, st));
     if (gc) PCS_CUDA(cudaMemcpyAsync(gc, p->gc, (size_t)p->C * 15 * 8, cudaMemcpyDeviceToHost, st));
     if (V) PCS_CUDA(cudaMemcpyAsync(V, p->V, (size_t)p->M * 36 * 8, cudaMemcpyDeviceToHost, st));

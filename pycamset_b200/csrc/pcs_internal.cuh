@@ -70,7 +70,7 @@ struct pcs_problem {
     double* uv = nullptr;
     // static tables
     double* tmpl = nullptr;        // [K][3] chain 0
-    double* tmpl4 = nullptr;       // [K][4] chain 0, padded rows for 16-byte loads (normal-equation kernel)
+    double* tmpl4 = nullptr;       // [K][4] points padded to 16-byte rows: the template (chain 0) or the free points (chain 1; refreshed by k_prepare_tables)
     int32_t* free_map = nullptr;   // [L]
     int32_t* free_idx = nullptr;   // [n_free] parameter-string position of free variable j
     uint16_t* cam_mask = nullptr;  // [C] bit k set = column k of [intr(9) extr(6)] is free
@@ -90,9 +90,15 @@ struct pcs_problem {
     int64_t* seg_start = nullptr;                      // [S+1] into the sorted observation arrays
     int32_t *s_key = nullptr, *s_cam = nullptr, *s_pose = nullptr;  // [N] sorted
     double* s_uv = nullptr;                            // [N][2] sorted
+    int32_t* obs_seg = nullptr;                        // [N] dd order: segment of every observation (residual kernel)
+    double* segtab = nullptr;                          // [S][SEG_STRIDE] per-segment combined transform (allocated on first use)
     // normal-equation outputs: one allocation [U | gc | cost | pad | V | gp | W]
     double* ne = nullptr;
     double *U = nullptr, *gc = nullptr, *cost = nullptr, *V = nullptr, *gp = nullptr, *W = nullptr;
+    // chain 1 (self-calibration), inside the same allocation between gp and W: point blocks Pk [K][3][3], gk [K][3] and the
+    // dense coupling tables Xck [C][K][15][3] (camera x point), Ymk [M][K][6][3] (pose x point); nullptr when the tables
+    // would be too large (block path unavailable: pcs_normal_dense remains)
+    double *Pk = nullptr, *gk = nullptr, *Xck = nullptr, *Ymk = nullptr;
     int64_t ne_doubles = 0;
     // dense path
     double* dense = nullptr;  // [n_free*n_free + n_free + 1]
@@ -132,10 +138,12 @@ namespace pcs {
 // kernels / launchers implemented in pcs_core.cu, used by pcs_solver.cu
 int launch_scatter_x(pcs_problem* p, const double* x_dev);
 int launch_prepare(pcs_problem* p, bool with_dR = false, const double* x_dev = nullptr, double* zero = nullptr,
-                   int64_t n_zero = 0);
+                   int64_t n_zero = 0, bool with_seg = false);
 int launch_residual(pcs_problem* p, double* r_dev);
 int launch_cost_only(pcs_problem* p, double* cost_dev);
 int launch_normal_blocks(pcs_problem* p, bool targets_cleared = false, int part = 0, int n_parts = 1);
+int launch_point_blocks(pcs_problem* p);   // chain 1: Pk, gk, Xck, Ymk (targets cleared by the prepare launch)
+inline int64_t ne_zero_doubles(const pcs_problem* p) { return p->W - p->ne; }   // everything accumulated with reductions precedes W
 int ensure_pinned(pcs_problem* p, int64_t doubles);
 void lm_free(pcs_problem* p);
 // pcs_schur.cu: S (n x n, column-major, lower) -= Z Z^T, Z column-major [k][n]

@@ -706,7 +706,7 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
 {
     // zero what is accumulated with reductions: [U | gc | cost | pad | V | gp]; W is fully overwritten
     if (!targets_cleared && part == 0) {
-        const int64_t zero_doubles = (p->V - p->ne) + (int64_t)p->M * 42;
+        const int64_t zero_doubles = ne_zero_doubles(p);
         PCS_CUDA(cudaMemsetAsync(p->ne, 0, (size_t)zero_doubles * sizeof(double), p->stream));
     }
     if (p->N == 0) return PCS_OK;

@@ -9,7 +9,10 @@
 //                    dense SPD solve (k_chol_solve, pcs_chol.cu; cuSOLVER for systems too large for it),
 //                    back-substitute the poses, move to the trial point and evaluate it with the full
 //                    normal-equation kernel into the second output set -- one host synchronisation per iteration;
-//   self-calibration: dense (n_free x n_free) normal matrix + cuSOLVER Cholesky, residual-only trial pass.
+//   self-calibration: the same step with the target points joining the cameras in the reduced system (15 C + 3 K
+//                    unknowns: point blocks Pk, camera x point blocks Xck on the A side, pose x point blocks Ymk next to W on
+//                    the coupling side); problems whose dense (camera, key) / (pose, key) tables would not fit fall back to the
+//                    dense (n_free x n_free) normal matrix + cuSOLVER Cholesky with a residual-only trial pass.
 // Marquardt scaling (lambda * diag(J^T J)) plays the role of x_scale='jac'; Nielsen's gain-ratio update
 // drives lambda.  Fixed parameters are rows / columns replaced by the identity.
 #include <cublas_v2.h>
@@ -189,10 +192,13 @@ k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict__ seg_cam, const
     }
 }
 
-// S = blockdiag(U masked + lambda D) with every other entry zero (each entry of S is written exactly once: no memset),
-// rhs = -gc masked, gc copy (for the convergence test); also clears the step scalars and the factorisation status.
-__global__ void k_lm_init_reduced(int C, int64_t nc, double lambda, const double* __restrict__ U, const double* __restrict__ gc,
-                                  const double* __restrict__ cost, const uint16_t* __restrict__ cam_mask, double* __restrict__ Smat,
+// S = [[U + lambda D, .], [Xck^T, Pk + lambda D]] (lower triangle; cameras first, then -- self-calibration chain -- the
+// target points), masked, every other entry zero (each entry of S is written exactly once: no memset); rhs = -g masked,
+// g copy (for the convergence test); also clears the step scalars and the factorisation status.
+__global__ void k_lm_init_reduced(int C, int K, int64_t nc, double lambda, const double* __restrict__ U, const double* __restrict__ gc,
+                                  const double* __restrict__ cost, const uint16_t* __restrict__ cam_mask,
+                                  const double* __restrict__ Pk, const double* __restrict__ gk, const double* __restrict__ Xck,
+                                  const uint8_t* __restrict__ key_mask, double* __restrict__ Smat,
                                   double* __restrict__ rhs, double* __restrict__ gcopy, double* __restrict__ cost_out,
                                   double* __restrict__ scal, int* __restrict__ info)
 {
@@ -201,20 +207,77 @@ __global__ void k_lm_init_reduced(int C, int64_t nc, double lambda, const double
     if (t == 8) { *info = 0; *cost_out = *cost; }
     if (t >= nc * nc) return;
     const int64_t col = t / nc, row = t % nc;      // column-major S
-    const int c = (int)(row / 15), a = (int)(row % 15), cb = (int)(col / 15), b = (int)(col % 15);
+    const int64_t n_cam = 15 * (int64_t)C;
     double v = 0.0;
-    if (c == cb) {
-        const unsigned mask = cam_mask[c];
-        const bool fa = mask & (1u << a), fb = mask & (1u << b);
-        v = (fa && fb) ? U[(int64_t)c * 225 + a * 15 + b] : 0.0;
-        if (a == b) {
-            // fixed rows: zero here, set to the identity after the all-reduce (k_lm_fix_diag)
-            v = fa ? v + lambda * v : 0.0;
-            rhs[row] = fa ? -gc[row] : 0.0;
-            gcopy[row] = fa ? gc[row] : 0.0;
+    if (row < n_cam && col < n_cam) {
+        const int c = (int)(row / 15), a = (int)(row % 15), cb = (int)(col / 15), b = (int)(col % 15);
+        if (c == cb) {
+            const unsigned mask = cam_mask[c];
+            const bool fa = mask & (1u << a), fb = mask & (1u << b);
+            v = (fa && fb) ? U[(int64_t)c * 225 + a * 15 + b] : 0.0;
+            if (a == b) {
+                // fixed rows: zero here, set to the identity after the all-reduce (k_lm_fix_diag)
+                v = fa ? v + lambda * v : 0.0;
+                rhs[row] = fa ? -gc[row] : 0.0;
+                gcopy[row] = fa ? gc[row] : 0.0;
+            }
         }
+    } else if (row >= n_cam && col >= n_cam) {
+        const int64_t jr = row - n_cam, jc = col - n_cam;
+        const int k = (int)(jr / 3), a = (int)(jr % 3), kb = (int)(jc / 3), b = (int)(jc % 3);
+        if (k == kb) {
+            const unsigned mask = key_mask[k];
+            const bool fa = mask & (1u << a), fb = mask & (1u << b);
+            v = (fa && fb) ? Pk[(int64_t)k * 9 + a * 3 + b] : 0.0;
+            if (a == b) {
+                v = fa ? v + lambda * v : 0.0;
+                rhs[row] = fa ? -gk[jr] : 0.0;
+                gcopy[row] = fa ? gk[jr] : 0.0;
+            }
+        }
+    } else if (row >= n_cam) {   // point row, camera column: Xck[c][k][i][a]
+        const int64_t jr = row - n_cam;
+        const int k = (int)(jr / 3), a = (int)(jr % 3), c = (int)(col / 15), i = (int)(col % 15);
+        if ((key_mask[k] & (1u << a)) && (cam_mask[c] & (1u << i))) v = Xck[(((int64_t)c * K + k) * 15 + i) * 3 + a];
     }
     Smat[t] = v;
+}
+
+// Point rows of Z (self-calibration chain): for every (pose, key) pair and point coordinate a, z = Ymk[m][k][:, a]^T L_m^-T,
+// scattered into the dense column-major Z next to the camera rows, and rhs[point row] -= z . y_m.  Pairs without
+// observations are all-zero blocks and are skipped (Z is cleared once: its sparsity pattern is static).
+__global__ void __launch_bounds__(256)
+k_lm_point_Z(int M, int K, int64_t nc, int64_t row0, const double* __restrict__ Ymk, const double* __restrict__ L,
+             const double* __restrict__ y, const uint8_t* __restrict__ pose_mask, const uint8_t* __restrict__ key_mask,
+             double* __restrict__ Z, double* __restrict__ rhs)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)M * K * 3) return;
+    const int a = (int)(t % 3);
+    const int64_t mk = t / 3;
+    const int k = (int)(mk % K), m = (int)(mk / K);
+    const double* Y = Ymk + mk * 18;
+    double w[6];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { w[i] = Y[3 * i + a]; any = any || (w[i] != 0.0); }
+    if (!any) return;
+    const bool row_free = key_mask[k] & (1u << a);
+    const unsigned pm = pose_mask[m];
+    const double* Lm = L + (int64_t)m * 36;
+    double z[6], dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = (row_free && (pm & (1u << i))) ? w[i] : 0.0;
+#pragma unroll
+        for (int q = 0; q < i; ++q) v -= Lm[i * 6 + q] * z[q];
+        z[i] = v / Lm[i * 6 + i];
+        dot = fma(z[i], y[(int64_t)m * 6 + i], dot);
+    }
+    const int64_t row = row0 + 3 * (int64_t)k + a;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Z[((int64_t)m * 6 + i) * nc + row] = z[i];
+    if (dot != 0.0) atomicAdd(rhs + row, -dot);
 }
 
 // rows whose diagonal is exactly zero after the reduction (fixed, or unobserved by every rank) -> identity
@@ -224,16 +287,31 @@ __global__ void k_lm_fix_diag(int64_t nc, double* __restrict__ Smat)
     if (a < nc && Smat[a * nc + a] == 0.0) Smat[a * nc + a] = 1.0;
 }
 
-// delta_p = L^-T (y - t)
-__global__ void k_lm_pose_back(int M, const double* __restrict__ L, const double* __restrict__ y, const double* __restrict__ t,
-                               double* __restrict__ delta_p)
+// delta_p = L^-T (y - Z_m^T delta_c), one warp per pose: the six dot products t_i = Z[:, 6 m + i] . delta_c (Z is
+// column-major with nc contiguous rows per pose column, so the lanes stride over one column: coalesced) are formed here
+// instead of by a library GEMV over the whole of Z, then lane 0 runs the 6 x 6 back substitution.
+__global__ void __launch_bounds__(128)
+k_lm_pose_back(int M, int64_t nc, const double* __restrict__ L, const double* __restrict__ y, const double* __restrict__ Z,
+               const double* __restrict__ delta_c, double* __restrict__ delta_p)
 {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (m >= M) return;
+    double t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double* Zm = Z + (int64_t)m * 6 * nc;
+    for (int64_t a = lane; a < nc; a += 32) {
+        const double d = delta_c[a];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t[i] = fma(Zm[i * nc + a], d, t[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[i] += __shfl_xor_sync(0xffffffffu, t[i], o);
+    if (lane != 0) return;
     const double* Lm = L + (int64_t)m * 36;
     double v[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) v[i] = y[(int64_t)m * 6 + i] - t[(int64_t)m * 6 + i];
+    for (int i = 0; i < 6; ++i) v[i] = y[(int64_t)m * 6 + i] - t[i];
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = v[i];
@@ -245,22 +323,24 @@ __global__ void k_lm_pose_back(int M, const double* __restrict__ L, const double
     for (int i = 0; i < 6; ++i) delta_p[(int64_t)m * 6 + i] = v[i];
 }
 
-// delta (parameter-string layout, template chain): [intr | extr | pose] from delta_c (15 per camera) and delta_p.
+// delta (parameter-string layout): [intr | extr | pose (| point)] from delta_A (15 per camera, then 3 per key) and delta_p.
 // Also accumulates pred = sum delta (lambda D delta + b), |delta|^2, |x|^2 and |g|_inf of the LOCAL pose part
-// plus (rank 0 only for the replicated camera norms) the camera part; D and b are this rank's partial sums.
-__global__ void k_lm_assemble_delta(int C, int M, double lambda, const double* __restrict__ dc, const double* __restrict__ dp,
+// plus (rank 0 only for the replicated camera / point norms) the replicated part; D and b are this rank's partial sums.
+__global__ void k_lm_assemble_delta(int C, int M, int K3, double lambda, const double* __restrict__ dc, const double* __restrict__ dp,
                                     const double* __restrict__ U, const double* __restrict__ gc, const double* __restrict__ V,
-                                    const double* __restrict__ gp, const uint16_t* __restrict__ cam_mask,
-                                    const uint8_t* __restrict__ pose_mask, const double* __restrict__ params,
+                                    const double* __restrict__ gp, const double* __restrict__ Pk, const double* __restrict__ gk,
+                                    const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask,
+                                    const uint8_t* __restrict__ key_mask, const double* __restrict__ params,
                                     double* __restrict__ delta, double* __restrict__ scal, int rank0)
 {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t total = 15 * (int64_t)C + 6 * (int64_t)M;
+    const int64_t n_cam = 15 * (int64_t)C, n_pose = 6 * (int64_t)M;
+    const int64_t total = n_cam + n_pose + K3;
     double pred = 0.0, dx2 = 0.0, x2 = 0.0, ginf = 0.0;
     if (t < total) {
         double d, D, g;
         bool replicated;
-        if (t < 15 * (int64_t)C) {
+        if (t < n_cam) {
             int c, a;
             if (t < 9 * (int64_t)C) { c = (int)(t / 9); a = (int)(t % 9); }
             else { c = (int)((t - 9 * (int64_t)C) / 6); a = 9 + (int)((t - 9 * (int64_t)C) % 6); }
@@ -269,14 +349,22 @@ __global__ void k_lm_assemble_delta(int C, int M, double lambda, const double* _
             D = f ? U[c * 225 + a * 16] : 0.0;
             g = f ? gc[c * 15 + a] : 0.0;
             replicated = true;
-        } else {
-            const int64_t r = t - 15 * (int64_t)C;
+        } else if (t < n_cam + n_pose) {
+            const int64_t r = t - n_cam;
             const int m = (int)(r / 6), a = (int)(r % 6);
             const bool f = pose_mask[m] & (1u << a);
             d = f ? dp[r] : 0.0;
             D = f ? V[(int64_t)m * 36 + a * 7] : 0.0;
             g = f ? gp[r] : 0.0;
             replicated = false;
+        } else {
+            const int64_t j = t - n_cam - n_pose;
+            const int k = (int)(j / 3), a = (int)(j % 3);
+            const bool f = key_mask[k] & (1u << a);
+            d = f ? dc[n_cam + j] : 0.0;
+            D = f ? Pk[(int64_t)k * 9 + a * 4] : 0.0;
+            g = f ? gk[j] : 0.0;
+            replicated = true;
         }
         delta[t] = d;
         pred = d * (lambda * D * d - g);
@@ -284,7 +372,7 @@ __global__ void k_lm_assemble_delta(int C, int M, double lambda, const double* _
             dx2 = d * d;
             x2 = params[t] * params[t];
         }
-        ginf = replicated ? 0.0 : fabs(g);  // camera gradient norm is taken from the all-reduced copy on the host side
+        ginf = replicated ? 0.0 : fabs(g);  // the replicated gradient norm is taken from the all-reduced copy (k_lm_take_step)
     }
     // block reduction
     __shared__ double sh[4][8];
@@ -422,8 +510,12 @@ static void swap_normal_buffers(pcs_problem* p, LmWorkspace* w)
 {
     double* other = (p->ne == w->ne_orig) ? w->ne_alt : w->ne_orig;
     const int64_t o_gc = p->gc - p->ne, o_cost = p->cost - p->ne, o_V = p->V - p->ne, o_gp = p->gp - p->ne, o_W = p->W - p->ne;
+    const int64_t o_P = p->Pk ? p->Pk - p->ne : 0, o_gk = p->Pk ? p->gk - p->ne : 0, o_X = p->Pk ? p->Xck - p->ne : 0,
+                  o_Y = p->Pk ? p->Ymk - p->ne : 0;
+    const bool pts = p->Pk != nullptr;
     p->ne = other; p->U = other; p->gc = other + o_gc; p->cost = other + o_cost; p->V = other + o_V; p->gp = other + o_gp;
     p->W = other + o_W;
+    if (pts) { p->Pk = other + o_P; p->gk = other + o_gk; p->Xck = other + o_X; p->Ymk = other + o_Y; }
 }
 
 void lm_free(pcs_problem* p)
@@ -477,8 +569,10 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
     PCS_CUDA(cudaMemsetAsync(w->delta, 0, (size_t)p->L * 8, p->stream));
     PCS_CUDA(cudaEventCreate(&w->ev0));
     PCS_CUDA(cudaEventCreate(&w->ev1));
-    if (p->chain == PCS_CHAIN_TEMPLATE) {
-        w->nc = 15 * (int64_t)p->C;
+    // PCS_LM_SELFCAL=dense forces the dense fallback of the self-calibration chain (A/B runs, tests)
+    static const bool force_dense = [] { const char* e = std::getenv("PCS_LM_SELFCAL"); return e && e[0] == 'd'; }();
+    if (p->chain == PCS_CHAIN_TEMPLATE || (p->Pk && !force_dense)) {
+        w->nc = 15 * (int64_t)p->C + (p->chain == PCS_CHAIN_SELFCAL ? 3 * (int64_t)p->K : 0);   // cameras (+ target points)
         w->np = 6 * (int64_t)p->M;
         PCS_CUDA(cudaMalloc((void**)&w->L, (size_t)p->M * 36 * 8));
         PCS_CUDA(cudaMalloc((void**)&w->y, (size_t)w->np * 8));
@@ -506,12 +600,13 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
     return PCS_OK;
 }
 
-// evaluate the normal equations at the current p->params (tables refreshed, reduction targets cleared in the same launch)
+// evaluate the block normal equations at the current p->params (tables refreshed, reduction targets cleared in the same launch)
 static int eval_normal(pcs_problem* p)
 {
-    if (p->chain != PCS_CHAIN_TEMPLATE) return PCS_ERR_UNSUPPORTED;
-    PCS_TRY(launch_prepare(p, false, nullptr, p->ne, (p->V - p->ne) + (int64_t)p->M * 42));
-    return launch_normal_blocks(p, true);
+    PCS_TRY(launch_prepare(p, false, nullptr, p->ne, ne_zero_doubles(p)));
+    PCS_TRY(launch_normal_blocks(p, true));
+    if (p->chain == PCS_CHAIN_SELFCAL) PCS_TRY(launch_point_blocks(p));
+    return PCS_OK;
 }
 
 // One damped solve at the current linearisation, enqueued without synchronising.  Afterwards w->delta holds the step
@@ -525,14 +620,19 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     double* rhs = w->red + nc * nc;
     double* gcopy = rhs + nc;
     double* cost_r = gcopy + nc;
-    k_lm_init_reduced<<<grid_for(std::max<int64_t>(nc * nc, 9), 256), 256, 0, st>>>(p->C, nc, lambda, p->U, p->gc, p->cost, p->cam_mask,
+    const bool selfcal = p->chain == PCS_CHAIN_SELFCAL;
+    k_lm_init_reduced<<<grid_for(std::max<int64_t>(nc * nc, 9), 256), 256, 0, st>>>(p->C, p->K, nc, lambda, p->U, p->gc, p->cost, p->cam_mask,
+                                                                                  p->Pk, p->gk, p->Xck, p->key_mask,
                                                                                   Smat, rhs, gcopy, cost_r, w->scal, w->info);
     k_lm_pose_factor<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, lambda, p->V, p->gp, p->pose_mask, w->L, w->y, w->scal);
     if (p->n_seg)
         k_lm_segment_Z<<<grid_for(p->n_seg * 15, 256), 256, 0, st>>>(p->n_seg, nc, p->seg_cam, p->seg_pose, p->W, w->L, w->y,
                                                                      p->cam_mask, p->pose_mask, w->Z, rhs);
+    if (selfcal)
+        k_lm_point_Z<<<grid_for((int64_t)p->M * p->K * 3, 256), 256, 0, st>>>(p->M, p->K, nc, 15 * (int64_t)p->C, p->Ymk, w->L, w->y,
+                                                                             p->pose_mask, p->key_mask, w->Z, rhs);
     PCS_CUDA(cudaGetLastError());
-    const double minus1 = -1.0, one = 1.0, zero = 0.0;
+    const double minus1 = -1.0, one = 1.0;
     static const bool lib_syrk = [] { const char* e = std::getenv("PCS_LM_SYRK"); return e && e[0] == 'c'; }();   // A/B runs
     if (lib_syrk) PCS_BLAS(cublasDsyrk(w->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, &one, Smat, (int)nc));
     else PCS_TRY(launch_schur_syrk(st, p->sm_count, nc, np, w->Z, Smat));
@@ -549,11 +649,12 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     }
     p->n_launches += 8;
     // rhs now holds delta_c
-    PCS_BLAS(cublasDgemv(w->blas, CUBLAS_OP_T, (int)nc, (int)np, &one, w->Z, (int)nc, rhs, 1, &zero, w->t, 1));
     double* dp = w->delta + 15 * (int64_t)p->C;  // pose part of the parameter-string delta is written in place
-    k_lm_pose_back<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, w->L, w->y, w->t, dp);
-    k_lm_assemble_delta<<<grid_for(15 * (int64_t)p->C + 6 * (int64_t)p->M, 128), 128, 0, st>>>(
-        p->C, p->M, lambda, rhs, dp, p->U, p->gc, p->V, p->gp, p->cam_mask, p->pose_mask, p->params, w->delta, w->scal, p->rank == 0);
+    k_lm_pose_back<<<grid_for((int64_t)p->M * 32, 128), 128, 0, st>>>(p->M, nc, w->L, w->y, w->Z, rhs, dp);
+    const int K3 = selfcal ? 3 * p->K : 0;
+    k_lm_assemble_delta<<<grid_for(15 * (int64_t)p->C + 6 * (int64_t)p->M + K3, 128), 128, 0, st>>>(
+        p->C, p->M, K3, lambda, rhs, dp, p->U, p->gc, p->V, p->gp, p->Pk, p->gk, p->cam_mask, p->pose_mask, p->key_mask, p->params,
+        w->delta, w->scal, p->rank == 0);
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;   // multi-rank: pred, |dx|^2, |x|^2 and the pose gradient norm are still rank-local here (k_lm_pack_scalars)
 }
@@ -584,10 +685,10 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
     PCS_CUDA(cudaSetDevice(p->device));
     pcs_lm_options o;
     if (opts_in) o = *opts_in; else pcs_lm_default_options(&o);
-    if (p->chain == PCS_CHAIN_SELFCAL && p->world > 1) {
-        // the dense self-calibration system is not combined across ranks: refuse instead of letting the replicated
+    if (p->chain == PCS_CHAIN_SELFCAL && p->world > 1 && !p->Pk) {
+        // the dense self-calibration fallback is not combined across ranks: refuse instead of letting the replicated
         // camera / point parameters diverge silently
-        set_error("pcs_lm_solve: the self-calibration chain is single-rank (world_size > 1 is supported for the template chain)");
+        set_error("pcs_lm_solve: the dense self-calibration fallback is single-rank");
         return PCS_ERR_UNSUPPORTED;
     }
     PCS_TRY(lm_prepare(p));
@@ -608,7 +709,7 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
         PCS_CUDA(cudaMalloc((void**)&w->comb, (size_t)(5 + p->world) * 8));
         w->comb_cap = 5 + p->world;
     }
-    const bool tmpl = p->chain == PCS_CHAIN_TEMPLATE;
+    const bool tmpl = w->nc > 0;   // block path (both chains); false: dense self-calibration fallback
     const int64_t n = p->n_free;
     int n_normal = 0, n_cost = 0, status = 0, it = 0;
     double lambda = o.lambda0, nu = 2.0;

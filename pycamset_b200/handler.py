@@ -144,10 +144,7 @@ class GpuBundleHandler:
 
     # ---- beyond the reference: normal equations and the LM solve on the device ------------------------
     def normal_equations(self, params):
-        if self.chain == L.CHAIN_TEMPLATE:
-            return self.problem.normal_equations(self._load(params))
-        JtJ, Jtr, cost = self.problem.normal_dense(self._load(params))
-        return dict(JtJ=JtJ, Jtr=Jtr, cost=cost)
+        return self.problem.normal_equations(self._load(params))
 
     def solve(self, x0=None, max_nfev=None, ftol=1e-8, xtol=1e-8, gtol=1e-8, verbose=0):
         if x0 is None:

@@ -173,7 +173,8 @@ class BundleProblem:
         return sc, sp, sl
 
     def normal_equations(self, x=None, with_W=True, out=None):
-        """Fused residual + Jacobian + J^T J / J^T r blocks (template chain).  Returns dict of host arrays.
+        """Fused residual + Jacobian + J^T J / J^T r blocks (both chains; the self-calibration chain adds the point blocks
+        Pk, gk, Xck, Ymk).  Returns dict of host arrays.
         `out` may hold preallocated (e.g. pinned) arrays U, gc, V, gp, W, cost_buf to receive the copies."""
         xk, xp = self._x(x)
         C, M, S = self.n_cams, self.n_poses, self.n_segments
@@ -189,7 +190,12 @@ class BundleProblem:
         cost = out.get("cost_buf", None)
         cost = np.empty(1) if cost is None else cost
         L.check(self._lib.pcs_normal_equations(self._h, xp, _ptr(U), _ptr(gc), _ptr(V), _ptr(gp), _ptr(W), _ptr(cost)))
-        return dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
+        res = dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
+        if self.chain == L.CHAIN_SELFCAL:
+            K = self.n_keys
+            res.update(Pk=np.empty((K, 3, 3)), gk=np.empty((K, 3)), Xck=np.empty((C, K, 15, 3)), Ymk=np.empty((M, K, 6, 3)))
+            L.check(self._lib.pcs_point_blocks(self._h, _ptr(res["Pk"]), _ptr(res["gk"]), _ptr(res["Xck"]), _ptr(res["Ymk"])))
+        return res
 
     def set_normal_precision(self, mixed: bool):
         """False (default): FP64 blocks.  True: gradients / cost / residual stay FP64, the J^T J blocks come from the

@@ -1,8 +1,9 @@
 """GPU: the persistent tiled Cholesky solve (csrc/pcs_chol.cu) against numpy on random SPD systems.
 
 Sizes cover one tile, ragged last tiles and odd leading dimensions (n = 15 C is rarely a multiple of 32), the bench
-size (480 = 32 cameras) and grids narrower than a phase's tile count (660 -> 252 tiles on 148 SMs).  Systems too
-large for the kernel's shared-memory row-block buffer (n > 672) are refused; pcs_lm_solve uses cuSOLVER there.  Tolerance: relative solution error
+size (480 = 32 cameras), grids narrower than a phase's tile count (660 -> 252 tiles on 148 SMs), and systems whose row
+blocks no longer fit the shared-memory buffer of the back substitution and stream through it in chunks (n = 700 ... 2100:
+1503 = the reduced system of the ccube self-calibration, 1920 = 128 cameras).  Tolerance: relative solution error
 <= 1e-9 * cond-scaled bound (the systems are built with cond ~ 1e4), residual <= 1e-11 relative."""
 import ctypes as ct
 
@@ -28,7 +29,7 @@ def _spd(n, rng):
     return (Q * d) @ Q.T
 
 
-@pytest.mark.parametrize("n", [1, 15, 32, 45, 64, 100, 255, 480, 495, 660])
+@pytest.mark.parametrize("n", [1, 15, 32, 45, 64, 100, 255, 480, 495, 660, 700, 1000, 1503, 1920, 2100])
 def test_spd_solve_matches_numpy(n):
     rng = np.random.default_rng(n)
     A = _spd(n, rng)
@@ -51,8 +52,13 @@ def test_spd_solve_flags_indefinite():
     assert rc == -5 and info == 1
 
 
-def test_spd_solve_refuses_oversized():
-    n = 1920
-    A = np.eye(n)
-    rc, _, _ = _solve(n, A, np.ones(n))
-    assert rc == -4
+def test_spd_solve_large_identity_and_odd_leading_dimension():
+    """n = 1921: odd leading dimension (guarded loads instead of 16-byte copies) with chunked row blocks."""
+    n = 1921
+    rng = np.random.default_rng(3)
+    A = np.eye(n) * 2.0
+    A[1:, 0] = A[0, 1:] = 1e-3 * rng.standard_normal(n - 1)
+    b = rng.standard_normal(n)
+    rc, info, x = _solve(n, A, b)
+    assert rc == 0 and info == 0
+    assert np.linalg.norm(A @ x - b) <= 1e-11 * (np.linalg.norm(A, 2) * np.linalg.norm(x) + np.linalg.norm(b))
