@@ -85,6 +85,7 @@ __global__ void k_prepare_tables(int C, int M, int64_t n_tail, double* __restric
                                  const int32_t* __restrict__ seg_pose, double* __restrict__ segtab, double* __restrict__ pts4)
 {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    pdl_launch_dependents();   // the evaluation kernel that follows may become resident now; it waits for this grid (pdl_wait)
     for (int64_t i = t; i < n_zero; i += (int64_t)gridDim.x * blockDim.x) zero[i] = 0.0;
     if (t < C) {
         const int64_t qi = 9 * t, ei = 9 * (int64_t)C + 6 * t;
@@ -204,8 +205,10 @@ k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __rest
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
+    // the observation stream is static: it is requested before the wait for the table set-up launch
     const int s = ld_stream_i32(obs_seg + i), k = ld_stream_i32(key + i);
     const double2 o = ld_stream_f64x2(uv + i);
+    pdl_wait();
     double T[SEG_STRIDE], q[10], Xt[4];
     {
         const double2* row = reinterpret_cast<const double2*>(segtab + (int64_t)s * SEG_STRIDE);
@@ -233,8 +236,9 @@ k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __rest
 int launch_residual(pcs_problem* p, double* r_dev)
 {
     if (p->N == 0) return PCS_OK;
-    k_residual<true><<<grid_for(p->N, 256), 256, 0, p->stream>>>(p->N, p->obs_seg, p->key, (const double2*)p->uv, p->segtab,
-                                                                p->camtab, p->tmpl4, (double2*)r_dev);
+    PCS_CUDA(launch_pdl(k_residual<true>, dim3(grid_for(p->N, 256)), dim3(256), 0, p->stream, p->N, (const int32_t*)p->obs_seg,
+                        (const int32_t*)p->key, (const double2*)p->uv, (const double*)p->segtab, (const double*)p->camtab,
+                        (const double*)p->tmpl4, (double2*)r_dev));
     ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;

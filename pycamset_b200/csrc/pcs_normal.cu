@@ -321,6 +321,8 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* ws = ne_smem + warp * NE_WARP_DOUBLES;
     const int wg = blockIdx.x * WARPS + warp;
+    pdl_launch_dependents();   // the exchange kernel of a pose-sharded evaluation may queue up behind this grid
+    pdl_wait();                // tables, cleared targets (k_prepare_tables) and the warp ranges are complete from here on
     if (wg >= n_warps) return;
 
     // this warp's range of whole segments (k_warp_ranges)
@@ -544,6 +546,8 @@ k_normal_mixed(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t*
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* ws = ne_smem + warp * NEM_WARP_DOUBLES;
     const int wg = blockIdx.x * WARPS + warp;
+    pdl_launch_dependents();
+    pdl_wait();
     if (wg >= n_warps) return;
     const int64_t sb = warp_seg[wg], se = warp_seg[wg + 1];
     if (sb >= se) return;
@@ -728,14 +732,11 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
     const int64_t* ranges = p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1);
-    if (mixed)
-        kern_mixed<<<grid, warps * 32, smem, p->stream>>>((int)n_warps, ranges, p->s_cam, p->s_pose, p->s_key,
-                                                                   (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
-                                                                   p->tmpl4, p->U, p->gc, p->cost, p->V, p->gp, p->W);
-    else
-        k_normal<5, 4, 1><<<grid, warps * 32, smem, p->stream>>>((int)n_warps, ranges, p->s_cam, p->s_pose, p->s_key,
-                                                                 (const double2*)p->s_uv, p->seg_start, p->camtab, p->posetab,
-                                                                 p->tmpl4, p->U, p->gc, p->cost, p->V, p->gp, p->W);
+    // programmatic dependent launch: the grid becomes resident while k_prepare_tables drains (pdl_wait inside the kernel)
+    PCS_CUDA(launch_pdl(mixed ? kern_mixed : k_normal<5, 4, 1>, dim3(grid), dim3(warps * 32), smem, p->stream, (int)n_warps, ranges,
+                        (const int32_t*)p->s_cam, (const int32_t*)p->s_pose, (const int32_t*)p->s_key, (const double2*)p->s_uv,
+                        (const int64_t*)p->seg_start, (const double*)p->camtab, (const double*)p->posetab, (const double*)p->tmpl4,
+                        p->U, p->gc, p->cost, p->V, p->gp, p->W));
     PCS_CUDA(cudaGetLastError());
     ++p->n_launches;
     if (p->timing) {

@@ -53,6 +53,7 @@ k_p2p_allreduce(double* __restrict__ local, int64_t n, int rank, int world_rt, P
     const int world = WORLD > 0 ? WORLD : world_rt;
     const int tid = threadIdx.x;
     const int64_t data = P2P_FLAG_DOUBLES + (int64_t)(epoch & 1) * world * n;
+    pdl_wait();   // launched behind the normal-equation kernel with programmatic serialisation: its sums are complete from here on
     for (int64_t i = tid; i < n; i += blockDim.x) {
         const double v = local[i];
 #pragma unroll
@@ -88,6 +89,7 @@ k_p2p_allreduce_multi(double* __restrict__ local, int64_t n, int rank, int world
     const int world = WORLD > 0 ? WORLD : world_rt;
     const int tid = threadIdx.x, b = blockIdx.x;   // gridDim.x == world
     const int64_t data = P2P_FLAG_DOUBLES + (int64_t)(epoch & 1) * world * n;
+    pdl_wait();
     {
         double* dst = peers.buf[b] + data + (int64_t)rank * n;
         const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(local)) & 15) == 0;
@@ -166,9 +168,10 @@ int pcs_p2p_allreduce_camera_blocks(pcs_problem* p)
     if (multi) {
         auto mk = st->world == 2 ? k_p2p_allreduce_multi<2> : st->world == 4 ? k_p2p_allreduce_multi<4>
                   : st->world == 8 ? k_p2p_allreduce_multi<8> : k_p2p_allreduce_multi<0>;
-        mk<<<st->world, 512, 0, p->stream>>>(p->U, st->n, st->rank, st->world, st->peers, st->epoch);
-    } else
-    kern<<<1, 1024, 0, p->stream>>>(p->U, st->n, st->rank, st->world, st->peers, st->epoch);
+        PCS_CUDA(launch_pdl(mk, dim3(st->world), dim3(512), 0, p->stream, p->U, st->n, st->rank, st->world, st->peers, st->epoch));
+    } else {
+        PCS_CUDA(launch_pdl(kern, dim3(1), dim3(1024), 0, p->stream, p->U, st->n, st->rank, st->world, st->peers, st->epoch));
+    }
     PCS_CUDA(cudaGetLastError());
     ++p->n_launches;
     return PCS_OK;

@@ -50,3 +50,27 @@ def test_real_reference_handler_through_the_cuda_closures(case):
     assert camset is not None and camset.get_n_cams() == int(g["n_cams"])      # built by the reference's own get_camset
     assert np.max(np.abs(loss_r(res.x) - res.fun)) < 1e-9                    # the reference agrees on the final residual
     gpu.close()
+
+
+def test_initialiser_drop_in_matches_the_reference():
+    """estimate_camera_relative_poses (template_handler.py:468-601): the reference's own function and the drop-in
+    (pycamset_b200.initialiser, cost evaluation on the GPU) on the same target / detection / camera objects."""
+    ra = _reference()
+    from pyCamSet import Camera, CameraSet, ChArUco
+    from pyCamSet.calibration_targets import TargetDetection
+    from pyCamSet.optimisation.template_handler import estimate_camera_relative_poses as ref_fn
+    from pyCamSet.utils.general_utils import make_4x4h_tform
+    from pycamset_b200 import synthetic as syn
+    from pycamset_b200.initialiser import estimate_camera_relative_poses as gpu_fn
+    C, M = 5, 9
+    rig = syn.make_rig(C, M, layout="dome", distortion=False, seed=3, detect_prob=0.9)
+    cams = CameraSet(camera_dict={f"cam_{i}": Camera(extrinsic=make_4x4h_tform(rig.extr[i, :3], rig.extr[i, 3:])) for i in range(C)})
+    for name in cams.get_names():
+        cams[name].name = name
+    target = ChArUco(10, 10, 4)
+    det = TargetDetection(cam_names=cams.get_names(), data=rig.dd(), max_ims=M)
+    a = ref_fn(target, det, cams)
+    b = gpu_fn(target, det, cams)
+    assert [x.shape for x in a] == [x.shape for x in b] and a[2].shape == (2 * M,)
+    assert np.max(np.abs(a[0] - b[0])) < 1e-12 and np.max(np.abs(a[1] - b[1])) < 1e-12
+    assert np.max(np.abs(a[2] - b[2]) / np.maximum(a[2], 1.0)) < 1e-9
