@@ -260,33 +260,33 @@ def _config1_rig(seed):
 
 
 def lm_e2e_handlers(seed, real_reference, max_nfev):
-    """name -> (handler, max_nfev): reference handler objects when the reference is importable, else the duck-typed
-    stand-ins of tests/fake_reference.py filled from the same data."""
+    """Yields (name, handler) one at a time: reference handler objects when the reference is importable, else the
+    duck-typed stand-ins of tests/fake_reference.py filled from the same data.  Lazily, and with max_nfev set right before
+    the hand-over: the reference's handlers share ONE options dict (DEFAULT_OPTIONS is aliased and mutated,
+    template_handler.py:108-110), so building a second handler changes the first one's max_nfev."""
     from tests.helpers import load_case
-    out = {}
-    if real_reference:
-        from baseline import reference_arm as ra
-        rig, x0 = _config1_rig(seed)
-        h = ra.ring_handlers(rig, "ring", x_template=x0)
-        h.problem_opts["max_nfev"] = max_nfev["config1_ring8x100"]
-        out["config1_ring8x100"] = h
-        for name, case in (("config2_ccube_template", "ccube_template"), ("config3_ccube_selfcal", "ccube_selfcal")):
-            out[name] = ra.golden_handler(load_case(case), max_nfev=max_nfev[name])
-    else:
-        from tests import fake_reference as fr
-        rig, x0 = _config1_rig(seed)
-        g = dict(dd=rig.dd(), template=rig.template, chain=0, n_cams=8, n_poses=100, x=x0,
-                 param0=np.concatenate([x0[:120], np.zeros(6), x0[120:]]),
-                 unfixed=np.concatenate([np.ones(120, bool), np.zeros(6, bool), np.ones(594, bool)]))
-        h = fr.TemplateBundleHandler(g)
-        h.problem_opts["max_nfev"] = max_nfev["config1_ring8x100"]
-        out["config1_ring8x100"] = h
-        for name, case in (("config2_ccube_template", "ccube_template"), ("config3_ccube_selfcal", "ccube_selfcal")):
-            g = load_case(case)
-            h = (fr.SelfBundleHandler if g["chain"] == 1 else fr.TemplateBundleHandler)(g)
-            h.problem_opts["max_nfev"] = max_nfev[name]
-            out[name] = h
-    return out
+    for name in LM_E2E_CASES:
+        if name == "config1_ring8x100":
+            rig, x0 = _config1_rig(seed)
+            if real_reference:
+                from baseline import reference_arm as ra
+                h = ra.ring_handlers(rig, "ring", x_template=x0)
+            else:
+                from tests import fake_reference as fr
+                g = dict(dd=rig.dd(), template=rig.template, chain=0, n_cams=8, n_poses=100, x=x0,
+                         param0=np.concatenate([x0[:120], np.zeros(6), x0[120:]]),
+                         unfixed=np.concatenate([np.ones(120, bool), np.zeros(6, bool), np.ones(594, bool)]))
+                h = fr.TemplateBundleHandler(g)
+        else:
+            g = load_case("ccube_template" if name == "config2_ccube_template" else "ccube_selfcal")
+            if real_reference:
+                from baseline import reference_arm as ra
+                h = ra.golden_handler(g, max_nfev=max_nfev[name])
+            else:
+                from tests import fake_reference as fr
+                h = (fr.SelfBundleHandler if g["chain"] == 1 else fr.TemplateBundleHandler)(g)
+        h.problem_opts["max_nfev"] = max_nfev[name]
+        yield name, h
 
 
 def lm_e2e_device(seed, device):
@@ -304,8 +304,7 @@ def lm_e2e_device(seed, device):
     else:
         out["handlers"] = "reference handler objects (baseline/_ref)"
     budget = {k: 100 for k in LM_E2E_CASES}           # the reference's max_nfev (template_handler.py:24-31)
-    hs = lm_e2e_handlers(seed, real, budget)
-    for name, h in hs.items():
+    for name, h in lm_e2e_handlers(seed, real, budget):
         try:
             run_bundle_adjustment(h, device=device)    # warm-up
             t0 = time.perf_counter()
@@ -327,7 +326,7 @@ def lm_e2e_reference(seed, threads):
     from baseline import reference_arm as ra
     budget = {"config1_ring8x100": 10, "config2_ccube_template": 100, "config3_ccube_selfcal": 100}
     out = {"handlers": "reference handler objects (baseline/_ref)"}
-    for name, h in lm_e2e_handlers(seed, True, budget).items():
+    for name, h in lm_e2e_handlers(seed, True, budget):
         try:
             res, dt = ra.run_ba(h, threads)
             out[name] = {"seconds": dt, "iterations": int(res.nfev), "iter_per_s": res.nfev / dt, "status": int(res.status),

@@ -181,6 +181,13 @@ PCS_API int pcs_set_allreduce(pcs_problem* p, pcs_allreduce_fn fn, void* user, i
 PCS_API int pcs_costfn(pcs_problem* p, int n_tables, const double* im_points, const double* proj, const double* intrinsics,
                        const double* dists, double* errors, double* per_image);
 
+/* Scale estimate of the self-calibration gauge transform: SelfBundleHandler.apply_gauge_transform
+ * (standard_bundle_handler.py:339-410, the cdist tables of :360-366).  Over all pairs i < j of visible points whose
+ * reference distance is np.isclose(., square_size, rtol, atol): *sum_ratio = sum d_ref / d_estimate, *n_pairs = their
+ * number (the reference's s is the mean).  Host buffers; estimate / reference [n_points][3], visible [n_points] bytes. */
+PCS_API int pcs_gauge_scale(int device, int64_t n_points, const double* estimate, const double* reference, const uint8_t* visible,
+                            double square_size, double rtol, double atol, double* sum_ratio, int64_t* n_pairs);
+
 /* Multi-GPU, raw evaluation: one-shot all-reduce (sum, rank order) of the camera blocks [U | gc | cost] over NVLink
  * peer memory -- the only exchange step of a pose-sharded normal-equation evaluation (C * 240 + 1 doubles, latency
  * bound).  Every rank allocates a zero-initialised buffer of pcs_p2p_buffer_bytes(p, world) that all peers have mapped

@@ -158,6 +158,23 @@ class GpuBundleHandler:
         x = self._load(x0)
         return self.problem.lm_solve(x, max_iter=max_nfev, ftol=ftol, xtol=xtol, gtol=gtol, verbose=verbose)
 
+    def get_camset(self, x):
+        """The reference handler's own get_camset(x) (camera objects are the reference's).  For the self-calibration
+        handler its post-solve gauge transform (standard_bundle_handler.py:339-410) is routed through
+        pycamset_b200.gauge for the duration of the call -- same arithmetic, the O(K^2) pair search on the GPU."""
+        h = self.handler
+        if not hasattr(h, "get_camset"):
+            return None
+        if not (hasattr(h, "apply_gauge_transform") and hasattr(h, "visible_feature_mask")):
+            return h.get_camset(x)
+        from . import gauge
+        device = self.problem.device
+        h.apply_gauge_transform = lambda proj, extr, poses, pts: gauge.apply_gauge_transform_for(h, proj, extr, poses, pts, device)
+        try:
+            return h.get_camset(x)
+        finally:
+            del h.apply_gauge_transform          # back to the class's method
+
     def close(self):
         self.problem.close()
 
@@ -208,9 +225,40 @@ def run_bundle_adjustment(param_handler, threads: int = 1, device: int = 0, solv
     logging.info(f"Optimisation took {end - start: .2f} seconds.")
     if final_euclid > 5:
         logging.critical("Remaining error is very large: please check the output results")
-    camset = handler.get_camset(result.x) if hasattr(handler, "get_camset") else None
+    camset = gpu.get_camset(result.x)
     if camset is not None and hasattr(camset, "set_calibration_history"):
         camset.set_calibration_history(result, handler)
+    return result, camset
+
+
+def run_bundle_adjustment_sharded(param_handler, device=None, group=None, ftol=1e-8, xtol=1e-8, gtol=1e-8):
+    """run_bundle_adjustment over the ranks of a torch.distributed process group, one process per GPU (template chain).
+
+    Every rank calls this with the same handler.  The observations are sharded by target pose, every rank eliminates its
+    own poses, the Schur-reduced camera system is all-reduced over NCCL and the pose blocks of the
+    solution are all-gathered, so `result.x` is the FULL free vector on every rank -- the same return contract as
+    run_bundle_adjustment: (result, camset)."""
+    import torch
+    from . import distributed as pdist
+    e = export_problem(param_handler)
+    if chain_id_from_blocks(e["blocks"]) != L.CHAIN_TEMPLATE:
+        raise L.PcsError(L.PCS_ERR_UNSUPPORTED, "the sharded entry point covers the template chain")
+    if not e["stock_mapping"]:
+        raise L.PcsError(L.PCS_ERR_UNSUPPORTED, "handlers that override get_bundle_adjustment_inputs must use the closures")
+    x0 = np.asarray(param_handler.get_initial_params(), np.float64)
+    params = np.asarray(param_handler.op_fun.build_param_list(*param_handler.get_bundle_adjustment_inputs(x0)), np.float64)
+    dd = e["dd"]
+    opts = getattr(param_handler, "problem_opts", {})
+    start = time.time()
+    full, st = pdist.lm_solve_sharded(dd[:, 0].astype(np.int32), dd[:, 1].astype(np.int32), dd[:, 2].astype(np.int32), dd[:, 3:5],
+                                      e["n_cams"], e["n_poses"], e["n_keys"], e["template"], params, e["unfixed"],
+                                      device=torch.cuda.current_device() if device is None else device, group=group,
+                                      max_iter=int(opts.get("max_nfev", 100)), ftol=ftol, xtol=xtol, gtol=gtol)
+    x = full[e["unfixed"]]
+    result = OptimizeResult(x=x, cost=st["cost_final"], nfev=st["n_eval_normal"] + st["n_eval_cost"], njev=st["n_eval_normal"],
+                            status=st["status"], success=st["status"] > 0, optimality=st["grad_norm_inf"],
+                            message="device Levenberg-Marquardt, pose-sharded", lm=st, seconds=time.time() - start)
+    camset = param_handler.get_camset(x) if hasattr(param_handler, "get_camset") else None
     return result, camset
 
 

@@ -74,3 +74,23 @@ def test_initialiser_drop_in_matches_the_reference():
     assert [x.shape for x in a] == [x.shape for x in b] and a[2].shape == (2 * M,)
     assert np.max(np.abs(a[0] - b[0])) < 1e-12 and np.max(np.abs(a[1] - b[1])) < 1e-12
     assert np.max(np.abs(a[2] - b[2]) / np.maximum(a[2], 1.0)) < 1e-9
+
+
+def test_gauge_transform_drop_in_matches_the_reference():
+    """SelfBundleHandler.apply_gauge_transform (standard_bundle_handler.py:339-410) on the ccube self-calibration fixture at
+    the reference's own final iterate: scale, points, poses and extrinsics from pycamset_b200.gauge (pair search on the GPU)
+    against the reference's method on copies of the same arrays."""
+    ra = _reference()
+    from pycamset_b200 import gauge
+    from tests.helpers import GOLDEN
+    g = load_case("ccube_selfcal")
+    h = ra.golden_handler(g)
+    x = np.load(GOLDEN / "ccube_selfcal_final.npz")["x_final"]
+    model = [np.array(a, np.float64).copy() for a in h.bundlePrimitive.return_bundle_primitives(x)]
+    ref = h.apply_gauge_transform(*[a.copy() for a in model])
+    got = gauge.apply_gauge_transform_for(h, *[a.copy() for a in model])
+    for a, b, name in zip(ref, got, ("proj", "extr", "poses", "points")):
+        assert np.all(np.isfinite(a)), name
+        assert np.max(np.abs(np.asarray(a) - np.asarray(b))) < 1e-9, name
+    # the transform preserves the calibration: residuals before and after agree
+    assert abs(np.linalg.norm(ref[3]) - np.linalg.norm(model[3])) > 0      # it did move the points
