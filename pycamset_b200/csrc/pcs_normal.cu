@@ -447,15 +447,19 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
 //     into pieces.  The fixed point of the LM iteration is defined by g = 0, so it is unchanged to FP64 accuracy.
 //   * J^T J only preconditions the step.  Each Jacobian entry is split into two BF16 terms, x ~ hi + lo (16 mantissa bits,
 //     truncation, relative error <= 2^-15), packed as (u-row, v-row) pairs -- exactly the k-pair a m16n8k16 fragment
-//     register holds -- and the Gram is hi^T hi + hi^T lo + lo^T hi: 6 HMMA.16816.F32.BF16 per 8 observations, FP32
-//     accumulators per SEGMENT (~40 observations), promoted to FP64 at the segment flush and summed in FP64 across
-//     segments.  Measured effect on the solver: tests/test_gpu_mixed_precision.py (same iterates' cost to 1e-6, same
+//     register holds -- and the Gram is the full product (hi + lo)^T (hi + lo): 8 HMMA.16816.F32.BF16 per 8
+//     observations, FP32 accumulators per SEGMENT (~40 observations), promoted to FP64 at the segment flush and summed
+//     in FP64 across segments.  All four terms are kept: the result is then the exact Gram matrix of a Jacobian whose
+//     entries are within 2^-15 of the true ones (a CONSISTENT perturbation, which Levenberg-Marquardt does not notice),
+//     up to FP32 accumulation.  Measured effect on the solver: tests/test_gpu_mixed_precision.py (same iterates' cost to 1e-6, same
 //     converged cost to 1e-9, iterations within 10 %).
 //   * A-fragment and B-fragment of a column tile are the same registers (as in the FP64 kernel): per k-step a lane loads
 //     4 x 8 bytes (hi / lo words of its two observations, columns g and g + 8 adjacent in the staged row).
 // ================================================================================================================
 constexpr int NEM_STAGE_DOUBLES = 512;   // 32 observations x 128 B: 16 hi words | 16 lo words (bf16 pairs (u, v))
-constexpr int NEM_GBUF_DOUBLES = 512;    // 32 x 16 FP64 gradient products
+constexpr int NEM_GSTRIDE = 18;          // row stride of the gradient-product table: 16-byte stores of 8 consecutive lanes and the
+                                         // 8-byte column reads of a half warp are both bank-conflict free without any swizzle
+constexpr int NEM_GBUF_DOUBLES = 32 * NEM_GSTRIDE;   // 32 x 16 FP64 gradient products (padded rows)
 constexpr int NEM_WARP_DOUBLES = NEM_STAGE_DOUBLES + NEM_GBUF_DOUBLES + NE_SCRATCH_DOUBLES;
 
 __device__ __forceinline__ void hmma_bf16(float d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
@@ -517,21 +521,20 @@ __device__ __forceinline__ void stage_rows_bf16(const NeRows& R, unsigned* __res
     stage_chunk(blk, swz, 3, hi, lo);
 }
 
-// the lane's 16 FP64 gradient products [J_u[a] r_u + J_v[a] r_v (a = 0..14) | r.r], parked in row `o` of the table
-// (pairs are stored as they are formed)
-__device__ __forceinline__ void store_grad_products(const NeRows& R, double* __restrict__ grow, int o)
+// the lane's 16 FP64 gradient products [J_u[a] r_u + J_v[a] r_v (a = 0..14) | r.r], parked in its row of the table
+// (pairs are stored as they are formed, at compile-time offsets)
+__device__ __forceinline__ void store_grad_products(const NeRows& R, double* __restrict__ grow)
 {
     const double ru = R.res[0], rv = R.res[1];
-    const int x = o & 7;
-    auto put = [&](int c, double p0, double p1) { *reinterpret_cast<double2*>(grow + ((c ^ x) << 1)) = make_double2(p0, p1); };
-    put(0, R.xD * ru, ru);
-    put(1, R.yD * rv, rv);
-    put(2, fma(R.Au[0], ru, R.Av[0] * rv), fma(R.Au[1], ru, R.Av[1] * rv));
-    put(3, fma(R.Au[2], ru, R.Av[2] * rv), fma(R.Au[3], ru, R.Av[3] * rv));
-    put(4, fma(R.Au[4], ru, R.Av[4] * rv), fma(R.Wc[0], ru, R.Wc[3] * rv));
-    put(5, fma(R.Wc[1], ru, R.Wc[4] * rv), fma(R.Wc[2], ru, R.Wc[5] * rv));
-    put(6, fma(R.Pm[0], ru, R.Pm[3] * rv), fma(R.Pm[1], ru, R.Pm[4] * rv));
-    put(7, fma(R.Pm[2], ru, R.Pm[5] * rv), fma(ru, ru, rv * rv));
+    double2* g2 = reinterpret_cast<double2*>(grow);
+    g2[0] = make_double2(R.xD * ru, ru);
+    g2[1] = make_double2(R.yD * rv, rv);
+    g2[2] = make_double2(fma(R.Au[0], ru, R.Av[0] * rv), fma(R.Au[1], ru, R.Av[1] * rv));
+    g2[3] = make_double2(fma(R.Au[2], ru, R.Av[2] * rv), fma(R.Au[3], ru, R.Av[3] * rv));
+    g2[4] = make_double2(fma(R.Au[4], ru, R.Av[4] * rv), fma(R.Wc[0], ru, R.Wc[3] * rv));
+    g2[5] = make_double2(fma(R.Wc[1], ru, R.Wc[4] * rv), fma(R.Wc[2], ru, R.Wc[5] * rv));
+    g2[6] = make_double2(fma(R.Pm[0], ru, R.Pm[3] * rv), fma(R.Pm[1], ru, R.Pm[4] * rv));
+    g2[7] = make_double2(fma(R.Pm[2], ru, R.Pm[5] * rv), fma(ru, ru, rv * rv));
 }
 
 template <int CTAS_PER_SM, int WARPS>
@@ -570,6 +573,13 @@ k_normal_mixed(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t*
     unsigned* const my_blk = stage + lane * 32;
     const int my_swz = nem_swz(lane);
     const int ga = lane & 15, gh = lane >> 4;
+    const double* const my_gcol = gbuf + 16 * gh * NEM_GSTRIDE + ga;   // column ga of this lane's half of the table
+    // fragment words of k-step 0 (hi / lo words of observations t4 and t4 + 4, columns g8 and g8 + 8); step ks adds 256 ks words
+    const int f_ch = g8 >> 1, f_wi = (g8 & 1) << 1, f_s0 = nem_swz(t4), f_s1 = nem_swz(t4 + 4);
+    const unsigned* const frag_h0 = stage + t4 * 32 + (((f_ch ^ f_s0) << 2) | f_wi);
+    const unsigned* const frag_l0 = stage + t4 * 32 + ((((4 + f_ch) ^ f_s0) << 2) | f_wi);
+    const unsigned* const frag_h1 = stage + (t4 + 4) * 32 + (((f_ch ^ f_s1) << 2) | f_wi);
+    const unsigned* const frag_l1 = stage + (t4 + 4) * 32 + ((((4 + f_ch) ^ f_s1) << 2) | f_wi);
 
     auto flush = [&]() {
         // FP32 segment sums -> FP64 fragments of the FP64 kernel's flush (aa = G[0:8,0:8], ab = G[0:8,8:16], bb = G[8:16,8:16]);
@@ -601,7 +611,7 @@ k_normal_mixed(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t*
         const int c = ob.c, m = ob.m;
         if (lane < cnt) {
             stage_rows_bf16(R, my_blk, my_swz);
-            store_grad_products(R, gbuf + lane * 16, lane);
+            store_grad_products(R, gbuf + lane * NEM_GSTRIDE);
         }
         int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
         if (lane == 0) { pc = last_c; pm = last_m; }
@@ -620,23 +630,36 @@ k_normal_mixed(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t*
                 if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
                 ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
             }
-            // gradient column sums of the piece: lane (ga, gh) adds the rows of its half
+            // gradient column sums of the piece: lane (ga, gh) adds the rows of its half that lie in [a, b) -- in quarters of
+            // four predicated loads issued back to back (four partial sums, compile-time offsets), so that the latency of a
+            // piece is a few shared-memory round trips instead of one per row
             {
-                const int r0 = max(a, 16 * gh), r1 = min(b, 16 * gh + 16);
-                for (int r = r0; r < r1; ++r) gacc += gbuf[r * 16 + ((((ga >> 1) ^ (r & 7)) << 1) | (ga & 1))];
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; q += 4) {
+                    const int lo = 16 * gh + q;
+                    if (lo + 4 > a && lo < b) {
+                        const double* gq = my_gcol + q * NEM_GSTRIDE;
+                        s0 += (lo >= a && lo < b) ? gq[0] : 0.0;
+                        s1 += (lo + 1 >= a && lo + 1 < b) ? gq[NEM_GSTRIDE] : 0.0;
+                        s2 += (lo + 2 >= a && lo + 2 < b) ? gq[2 * NEM_GSTRIDE] : 0.0;
+                        s3 += (lo + 3 >= a && lo + 3 < b) ? gq[3 * NEM_GSTRIDE] : 0.0;
+                    }
+                }
+                gacc += (s0 + s1) + (s2 + s3);
             }
-            // Gram k-steps (8 observations each) of the piece; steps shared with a neighbouring piece are masked
-            for (int ks = a >> 3; ks <= (b - 1) >> 3; ++ks) {
-                const int o0 = 8 * ks + t4, o1 = o0 + 4;
-                const unsigned* b0p = stage + o0 * 32;
-                const unsigned* b1p = stage + o1 * 32;
-                const int ch = g8 >> 1, wi = (g8 & 1) << 1;
-                const int s0 = nem_swz(o0), s1 = nem_swz(o1);
-                uint2 h0 = *reinterpret_cast<const uint2*>(b0p + (((ch ^ s0) << 2) | wi));
-                uint2 l0 = *reinterpret_cast<const uint2*>(b0p + ((((4 + ch) ^ s0) << 2) | wi));
-                uint2 h1 = *reinterpret_cast<const uint2*>(b1p + (((ch ^ s1) << 2) | wi));
-                uint2 l1 = *reinterpret_cast<const uint2*>(b1p + ((((4 + ch) ^ s1) << 2) | wi));
+            // Gram k-steps (8 observations each) of the piece, unrolled: the fragment addresses of a step are the lane's four
+            // constants plus a compile-time offset.  Steps outside the piece are skipped (warp-uniform), steps shared with a
+            // neighbouring piece are masked.
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                if (8 * ks + 8 <= a || 8 * ks >= b) continue;
+                uint2 h0 = *reinterpret_cast<const uint2*>(frag_h0 + ks * 256);
+                uint2 l0 = *reinterpret_cast<const uint2*>(frag_l0 + ks * 256);
+                uint2 h1 = *reinterpret_cast<const uint2*>(frag_h1 + ks * 256);
+                uint2 l1 = *reinterpret_cast<const uint2*>(frag_l1 + ks * 256);
                 if (8 * ks < a || 8 * ks + 8 > b) {
+                    const int o0 = 8 * ks + t4, o1 = o0 + 4;
                     if (o0 < a || o0 >= b) { h0 = make_uint2(0u, 0u); l0 = make_uint2(0u, 0u); }
                     if (o1 < a || o1 >= b) { h1 = make_uint2(0u, 0u); l1 = make_uint2(0u, 0u); }
                 }
@@ -648,6 +671,11 @@ k_normal_mixed(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t*
                 hmma_bf16(D1, h0.x, h0.y, h1.x, h1.y, l0.y, l1.y);
                 hmma_bf16(D0, l0.x, l0.y, l1.x, l1.y, h0.x, h1.x);
                 hmma_bf16(D1, l0.x, l0.y, l1.x, l1.y, h0.y, h1.y);
+                // lo^T lo: 2^-16 of the result, but without it the sum is (H + L)^T (H + L) MINUS a positive semi-definite
+                // matrix -- no longer the Gram matrix of any Jacobian -- and the Schur complement of the LM step, which lives
+                // on cancellation between U, W and V, degrades: 66 instead of 17 iterations on the ring5 golden (measured)
+                hmma_bf16(D0, l0.x, l0.y, l1.x, l1.y, l0.x, l1.x);
+                hmma_bf16(D1, l0.x, l0.y, l1.x, l1.y, l0.y, l1.y);
             }
         }
         __syncwarp();

@@ -554,12 +554,26 @@ static int lm_prepare(pcs_problem* p)
     return rc;
 }
 
-static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
+// The library handles are created only where a library path is actually taken (the dense self-calibration fallback, a
+// reduced system too large for the persistent Cholesky kernel, or the PCS_LM_CHOL / PCS_LM_SYRK A/B switches): creating
+// them costs tens to hundreds of milliseconds per problem, more than a whole solve of a small calibration.
+static int ensure_solver(pcs_problem* p, LmWorkspace* w)
 {
-    PCS_BLAS(cublasCreate(&w->blas));
-    PCS_BLAS(cublasSetStream(w->blas, p->stream));
+    if (w->solver) return PCS_OK;
     PCS_SOLVER(cusolverDnCreate(&w->solver));
     PCS_SOLVER(cusolverDnSetStream(w->solver, p->stream));
+    return PCS_OK;
+}
+static int ensure_blas(pcs_problem* p, LmWorkspace* w)
+{
+    if (w->blas) return PCS_OK;
+    PCS_BLAS(cublasCreate(&w->blas));
+    PCS_BLAS(cublasSetStream(w->blas, p->stream));
+    return PCS_OK;
+}
+
+static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
+{
     PCS_CUDA(cudaMalloc((void**)&w->delta, (size_t)p->L * 8));
     PCS_CUDA(cudaMalloc((void**)&w->backup, (size_t)p->L * 8));
     PCS_CUDA(cudaMalloc((void**)&w->scal, 8 * 8));
@@ -581,10 +595,13 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
         PCS_CUDA(cudaMemsetAsync(w->Z, 0, (size_t)(w->nc * w->np) * 8, p->stream));  // sparsity pattern is static
         w->red_doubles = w->nc * w->nc + 2 * w->nc + 1;
         PCS_CUDA(cudaMalloc((void**)&w->red, (size_t)w->red_doubles * 8));
-        PCS_SOLVER(cusolverDnDpotrf_bufferSize(w->solver, CUBLAS_FILL_MODE_LOWER, (int)w->nc, w->red, (int)w->nc, &w->lwork));
         // own persistent Cholesky solve (PCS_LM_CHOL=cusolver selects the library path for A/B runs)
         const char* e = std::getenv("PCS_LM_CHOL");
         if (!(e && e[0] == 'c')) PCS_TRY(chol_prepare(p->device, w->nc, &w->Ldiag, &w->bar, &w->chol_grid));
+        if (w->chol_grid == 0) {
+            PCS_TRY(ensure_solver(p, w));
+            PCS_SOLVER(cusolverDnDpotrf_bufferSize(w->solver, CUBLAS_FILL_MODE_LOWER, (int)w->nc, w->red, (int)w->nc, &w->lwork));
+        }
         PCS_CUDA(cudaMalloc((void**)&w->ne_alt, (size_t)p->ne_doubles * 8));
         w->ne_orig = p->ne;
     } else {
@@ -594,6 +611,7 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
         w->H = p->dense;
         PCS_CUDA(cudaMalloc((void**)&w->Hd, (size_t)(n * n) * 8));
         PCS_CUDA(cudaMalloc((void**)&w->rhs, (size_t)n * 8));
+        PCS_TRY(ensure_solver(p, w));
         PCS_SOLVER(cusolverDnDpotrf_bufferSize(w->solver, CUBLAS_FILL_MODE_LOWER, (int)n, w->Hd, (int)n, &w->lwork));
     }
     PCS_CUDA(cudaMalloc((void**)&w->work, (size_t)std::max(w->lwork, 1) * 8));
@@ -634,6 +652,7 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     PCS_CUDA(cudaGetLastError());
     const double minus1 = -1.0, one = 1.0;
     static const bool lib_syrk = [] { const char* e = std::getenv("PCS_LM_SYRK"); return e && e[0] == 'c'; }();   // A/B runs
+    if (lib_syrk) PCS_TRY(ensure_blas(p, w));
     if (lib_syrk) PCS_BLAS(cublasDsyrk(w->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, &one, Smat, (int)nc));
     else PCS_TRY(launch_schur_syrk(st, p->sm_count, nc, np, w->Z, Smat));
     if (p->allreduce) {

@@ -125,7 +125,7 @@ def test_invalid_input_raises():
             p.residual(np.zeros(3))
     with BundleProblem(1, rig.cam.numpy(), pose, key, uv, 4, 6, 81) as p:                  # self-calibration chain
         with pytest.raises(_lib.PcsError, match="template chain"):
-            p.normal_equations()
+            p.set_normal_precision(True)                                                   # the mixed kernel is chain 0 only
 
 
 def test_lm_alternating_problem_sizes_keep_the_cholesky_shared_memory_optin():
