@@ -140,8 +140,12 @@ __global__ void k_prepare_tables(int C, int M, int64_t n_tail, double* __restric
                 o[SEG_R + 3 * a + b] = fma(Rc[3 * a], Rm[b], fma(Rc[3 * a + 1], Rm[3 + b], Rc[3 * a + 2] * Rm[6 + b]));
             o[SEG_T + a] = fma(Rc[3 * a], em[3], fma(Rc[3 * a + 1], em[4], fma(Rc[3 * a + 2], em[5], ec[3 + a])));
         }
-        o[SEG_CAM] = __hiloint2double(0, c);
-        o[SEG_CAM + 1] = 0.0;
+        for (int k = 0; k < 9; ++k) {
+            const int64_t iq = 9 * (int64_t)c + k;
+            const int32_t fq = x ? free_map[iq] : -1;
+            o[SEG_Q + k] = fq >= 0 ? x[fq] : params[iq];
+        }
+        o[SEG_Q + 9] = 0.0;
     }
 }
 
@@ -180,9 +184,9 @@ static inline const double* points_ptr(const pcs_problem* p)
 // ------------------------------------------------------------------------------------------------
 // K_res: residual, one thread per observation, dd row order.  44 algorithmic bytes / observation.
 // ------------------------------------------------------------------------------------------------
-// Rows of the per-segment table and the camera table are fetched with 16-byte loads; the observation stream (segment id,
-// key, (u, v)) is read once and bypasses L1 allocation.  Per lane: 12 + 10 + 3..4 doubles of table rows instead of the
-// 34 + 3 of a separate pose and camera transform -- the kernel is bound by the bytes every lane has to RECEIVE through
+// Rows of the per-segment table are fetched with 16-byte loads; the observation stream (segment id, key, (u, v)) is read
+// once and bypasses L1 allocation.  Per lane: 22 + 4 doubles of table rows instead of the 34 + 3 of a separate pose and
+// camera transform, in one dependent load level -- the kernel is bound by the bytes every lane has to RECEIVE through
 // the L1 data pipe (128 B / clock / SM), not by HBM, so fewer row bytes per observation is what makes it faster.
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p)
 {
@@ -209,7 +213,7 @@ k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __rest
     const int s = ld_stream_i32(obs_seg + i), k = ld_stream_i32(key + i);
     const double2 o = ld_stream_f64x2(uv + i);
     pdl_wait();
-    double T[SEG_STRIDE], q[10], Xt[4];
+    double T[SEG_STRIDE], Xt[4];
     {
         const double2* row = reinterpret_cast<const double2*>(segtab + (int64_t)s * SEG_STRIDE);
 #pragma unroll
@@ -222,14 +226,10 @@ k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __rest
             const double* pt = pts + 3 * (int64_t)k;
             Xt[0] = pt[0]; Xt[1] = pt[1]; Xt[2] = pt[2];
         }
-        const int c = __double2loint(T[SEG_CAM]);
-        const double2* qr = reinterpret_cast<const double2*>(camtab + (int64_t)c * CAM_STRIDE + CAM_Q);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) { const double2 v = qr[j]; q[2 * j] = v.x; q[2 * j + 1] = v.y; }
     }
     double Xc[3];
     transform(T + SEG_R, T + SEG_T, Xt, Xc);
-    const Proj p = project(q, Xc);
+    const Proj p = project(T + SEG_Q, Xc);
     r_out[i] = make_double2(p.u - o.x, p.v - o.y);
 }
 

@@ -27,8 +27,9 @@ namespace pcs {
 constexpr int CAM_Q = 0, CAM_R = 9, CAM_T = 18, CAM_JL = 21, CAM_STRIDE = 32;
 // Per-pose table row: [R(9) | t(3) | Jl(9) | pad(3)] = 24 doubles.
 constexpr int POSE_R = 0, POSE_T = 9, POSE_JL = 12, POSE_STRIDE = 24;
-// Per-segment (camera, pose) row of the residual kernel: [R_c R_m (9) | R_c t_m + t_c (3) | camera index (int32 bits) | pad] = 14 doubles.
-constexpr int SEG_R = 0, SEG_T = 9, SEG_CAM = 12, SEG_STRIDE = 14;
+// Per-segment (camera, pose) row of the residual kernel: [R_c R_m (9) | R_c t_m + t_c (3) | intrinsics q (9) | pad] = 22 doubles:
+// everything an observation of the segment needs sits in ONE row (one dependent load level after the segment id).
+constexpr int SEG_R = 0, SEG_T = 9, SEG_Q = 12, SEG_STRIDE = 22;
 
 __device__ __forceinline__ void rodrigues(const double r[3], double R[9])
 {
