@@ -32,7 +32,9 @@ namespace pcs {
 struct LmWorkspace {
     cublasHandle_t blas = nullptr;
     cusolverDnHandle_t solver = nullptr;
-    int64_t nc = 0;          // 15 C
+    int64_t nc = 0;          // order of the reduced system: 15 C (+ 3 K), rounded up to a multiple of 32 (identity rows) so that every
+                             // tile of the Cholesky kernel is full and moves with 16-byte copies, whatever C and K are
+    int64_t nl = 0;          // logical order 15 C (+ 3 K)
     int64_t np = 0;          // 6 M
     double* L = nullptr;     // [M][36] lower Cholesky factors of damped V
     double* y = nullptr;     // [M][6]  L^-1 b_p
@@ -195,7 +197,7 @@ k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict__ seg_cam, const
 // S = [[U + lambda D, .], [Xck^T, Pk + lambda D]] (lower triangle; cameras first, then -- self-calibration chain -- the
 // target points), masked, every other entry zero (each entry of S is written exactly once: no memset); rhs = -g masked,
 // g copy (for the convergence test); also clears the step scalars and the factorisation status.
-__global__ void k_lm_init_reduced(int C, int K, int64_t nc, double lambda, const double* __restrict__ U, const double* __restrict__ gc,
+__global__ void k_lm_init_reduced(int C, int K, int64_t nc, int64_t nl, double lambda, const double* __restrict__ U, const double* __restrict__ gc,
                                   const double* __restrict__ cost, const uint16_t* __restrict__ cam_mask,
                                   const double* __restrict__ Pk, const double* __restrict__ gk, const double* __restrict__ Xck,
                                   const uint8_t* __restrict__ key_mask, double* __restrict__ Smat,
@@ -209,7 +211,9 @@ __global__ void k_lm_init_reduced(int C, int K, int64_t nc, double lambda, const
     const int64_t col = t / nc, row = t % nc;      // column-major S
     const int64_t n_cam = 15 * (int64_t)C;
     double v = 0.0;
-    if (row < n_cam && col < n_cam) {
+    if (row >= nl || col >= nl) {       // padding rows: zero here, identity after the all-reduce (k_lm_fix_diag)
+        if (row == col) { rhs[row] = 0.0; gcopy[row] = 0.0; }
+    } else if (row < n_cam && col < n_cam) {
         const int c = (int)(row / 15), a = (int)(row % 15), cb = (int)(col / 15), b = (int)(col % 15);
         if (c == cb) {
             const unsigned mask = cam_mask[c];
@@ -586,7 +590,8 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
     // PCS_LM_SELFCAL=dense forces the dense fallback of the self-calibration chain (A/B runs, tests)
     static const bool force_dense = [] { const char* e = std::getenv("PCS_LM_SELFCAL"); return e && e[0] == 'd'; }();
     if (p->chain == PCS_CHAIN_TEMPLATE || (p->Pk && !force_dense)) {
-        w->nc = 15 * (int64_t)p->C + (p->chain == PCS_CHAIN_SELFCAL ? 3 * (int64_t)p->K : 0);   // cameras (+ target points)
+        w->nl = 15 * (int64_t)p->C + (p->chain == PCS_CHAIN_SELFCAL ? 3 * (int64_t)p->K : 0);   // cameras (+ target points)
+        w->nc = (w->nl + 31) / 32 * 32;
         w->np = 6 * (int64_t)p->M;
         PCS_CUDA(cudaMalloc((void**)&w->L, (size_t)p->M * 36 * 8));
         PCS_CUDA(cudaMalloc((void**)&w->y, (size_t)w->np * 8));
@@ -639,7 +644,7 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     double* gcopy = rhs + nc;
     double* cost_r = gcopy + nc;
     const bool selfcal = p->chain == PCS_CHAIN_SELFCAL;
-    k_lm_init_reduced<<<grid_for(std::max<int64_t>(nc * nc, 9), 256), 256, 0, st>>>(p->C, p->K, nc, lambda, p->U, p->gc, p->cost, p->cam_mask,
+    k_lm_init_reduced<<<grid_for(std::max<int64_t>(nc * nc, 9), 256), 256, 0, st>>>(p->C, p->K, nc, w->nl, lambda, p->U, p->gc, p->cost, p->cam_mask,
                                                                                   p->Pk, p->gk, p->Xck, p->key_mask,
                                                                                   Smat, rhs, gcopy, cost_r, w->scal, w->info);
     k_lm_pose_factor<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, lambda, p->V, p->gp, p->pose_mask, w->L, w->y, w->scal);

@@ -142,3 +142,62 @@ def test_two_gpus_nccl_match_single_rank():
     g = np.load(out)
     assert abs(float(g["cost_final"]) - st_s["cost_final"]) <= 1e-10 * st_s["cost_final"]
     assert np.max(np.abs(g["x"] - x_s) / np.maximum(1.0, np.abs(x_s))) <= 1e-9
+
+
+def test_two_ranks_self_calibration_chain():
+    """The self-calibration chain on the block path, pose-sharded: the target points are replicated like the cameras (their
+    blocks are partial sums that enter the all-reduced system), the poses are local.  Same iterates as the single-rank
+    solve.  (The dense fallback refuses world_size > 1)"""
+    from pycamset_b200 import distributed as pdist
+    from pycamset_b200.problem import BundleProblem
+    from tests.helpers import load_case
+    g = load_case("ring5_fixedcam_selfcal")
+    dd = g["dd"]
+    Cn, Mn, Kn = int(g["n_cams"]), int(g["n_poses"]), g["template"].shape[0]
+    cam, pose, key, uv = dd[:, 0].astype(np.int32), dd[:, 1].astype(np.int32), dd[:, 2].astype(np.int32), dd[:, 3:5].copy()
+    params, unfixed = g["param0"], np.asarray(g["unfixed"], bool)
+
+    def solve_single(iters):
+        with BundleProblem(1, cam, pose, key, uv, Cn, Mn, Kn, unfixed=unfixed) as p:
+            p.set_param_string(params)
+            x, st = p.lm_solve(g["x"], max_iter=iters, ftol=0.0, xtol=0.0, gtol=0.0)
+            return p.get_param_string(), st
+
+    ranges = pdist.balanced_pose_ranges(np.bincount(pose, minlength=Mn), 2)
+
+    def solve_sharded(iters):
+        hs = _HostSum(2)
+        out, err = [None, None], []
+
+        def worker(r):
+            try:
+                c_s, p_s, k_s, uv_s = pdist.shard_observations(cam, pose, key, uv, ranges[r])
+                par = pdist.shard_param_string(params, Cn, Mn, ranges[r], n_keys=Kn)
+                unf = pdist.shard_param_string(unfixed, Cn, Mn, ranges[r], n_keys=Kn).astype(bool)
+                with BundleProblem(1, c_s, p_s, k_s, uv_s, Cn, ranges[r][1] - ranges[r][0], Kn, unfixed=unf) as p:
+                    p.set_param_string(par)
+                    p.set_allreduce(hs.hook(r), r, 2)
+                    _, st = p.lm_solve(par[unf], max_iter=iters, ftol=0.0, xtol=0.0, gtol=0.0)
+                    out[r] = (p.get_param_string(), st)
+            except Exception as e:  # pragma: no cover
+                err.append(e)
+                hs.barrier.abort()
+
+        ts = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+        [t.start() for t in ts]
+        [t.join(timeout=600) for t in ts]
+        assert not err, err
+        (p0, st0), (p1, st1) = out
+        C15 = 15 * Cn
+        full = np.concatenate([p0[:C15], p0[C15:C15 + 6 * (ranges[0][1] - ranges[0][0])], p1[C15:C15 + 6 * (ranges[1][1] - ranges[1][0])],
+                               p0[C15 + 6 * (ranges[0][1] - ranges[0][0]):]])
+        assert np.array_equal(p0[:C15], p1[:C15])                                    # cameras replicated
+        assert np.array_equal(p0[-3 * Kn:], p1[-3 * Kn:])                            # points replicated
+        return full, st0, st1
+
+    for iters in (1, 3):
+        ref, st = solve_single(iters)
+        full, st0, st1 = solve_sharded(iters)
+        assert st0["iterations"] == st1["iterations"] == st["iterations"]
+        assert abs(st0["cost_final"] - st["cost_final"]) <= 1e-9 * st["cost_final"], (st0, st)
+        assert np.max(np.abs(full - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-8
