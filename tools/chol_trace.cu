@@ -20,7 +20,7 @@ int main(int argc, char** argv)
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms = 0;
     // warm the clocks up: ~0.5 s of back-to-back solves before the traced one
-    for (int rep = 0; rep < 2000; ++rep) launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, &bar_base, info, nullptr);
+    for (int rep = 0; rep < (n > 700 ? 200 : 2000); ++rep) launch_chol_solve(nullptr, grid, n, dA, n, db, Ldiag, bar, &bar_base, info, nullptr);
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int rep = 0; rep < 20; ++rep) {
