@@ -201,69 +201,45 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p)
     return v;
 }
 
-// Persistent, software-pipelined: the grid is sized to the machine and every thread walks observations i, i + T, i + 2T ...
-// While observation n is evaluated, the stream entries of observation n + 1 are already in registers and its table rows
-// (one 176-byte segment row, one 32-byte point row) have been requested into L1 with prefetch instructions -- the two
-// dependent memory round trips (HBM for the stream, L2 for the rows) of the next observation hide behind the arithmetic
-// of the current one.  ncu on the one-observation-per-thread form: 82 % of the stall samples were long-scoreboard waits
-// at 48 resident warps per SM.
+// One thread per observation (a persistent, software-pipelined variant -- next observation's stream entries in registers,
+// its rows prefetched into L1 -- was measured at 67 us against 32 us: 60 registers, half the resident warps, L1 hit rate
+// down to 50 %; not kept).
 template <bool PTS4>
 __global__ void __launch_bounds__(256)
 k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __restrict__ key, const double2* __restrict__ uv,
            const double* __restrict__ segtab, const double* __restrict__ camtab, const double* __restrict__ pts,
            double2* __restrict__ r_out)
 {
-    const int64_t T = (int64_t)gridDim.x * blockDim.x;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
-    // the observation stream is static: the first entries are requested before the wait for the table set-up launch
-    int s = ld_stream_i32(obs_seg + i), k = ld_stream_i32(key + i);
-    double2 o = ld_stream_f64x2(uv + i);
+    // the observation stream is static: it is requested before the wait for the table set-up launch
+    const int s = ld_stream_i32(obs_seg + i), k = ld_stream_i32(key + i);
+    const double2 o = ld_stream_f64x2(uv + i);
     pdl_wait();
-    for (; i < N; i += T) {
-        const int64_t in = i + T;
-        int s_n = 0, k_n = 0;
-        double2 o_n = make_double2(0.0, 0.0);
-        if (in < N) { s_n = ld_stream_i32(obs_seg + in); k_n = ld_stream_i32(key + in); o_n = ld_stream_f64x2(uv + in); }
-        double Tr[SEG_STRIDE], Xt[4];
-        {
-            const double2* row = reinterpret_cast<const double2*>(segtab + (int64_t)s * SEG_STRIDE);
+    double T[SEG_STRIDE], Xt[4];
+    {
+        const double2* row = reinterpret_cast<const double2*>(segtab + (int64_t)s * SEG_STRIDE);
 #pragma unroll
-            for (int j = 0; j < SEG_STRIDE / 2; ++j) { const double2 v = row[j]; Tr[2 * j] = v.x; Tr[2 * j + 1] = v.y; }
-            if (PTS4) {   // rows padded to 4 doubles
-                const double2* x2 = reinterpret_cast<const double2*>(pts + 4 * (int64_t)k);
-                const double2 a = x2[0], b = x2[1];
-                Xt[0] = a.x; Xt[1] = a.y; Xt[2] = b.x;
-            } else {
-                const double* pt = pts + 3 * (int64_t)k;
-                Xt[0] = pt[0]; Xt[1] = pt[1]; Xt[2] = pt[2];
-            }
+        for (int j = 0; j < SEG_STRIDE / 2; ++j) { const double2 v = row[j]; T[2 * j] = v.x; T[2 * j + 1] = v.y; }
+        if (PTS4) {   // rows padded to 4 doubles
+            const double2* x2 = reinterpret_cast<const double2*>(pts + 4 * (int64_t)k);
+            const double2 a = x2[0], b = x2[1];
+            Xt[0] = a.x; Xt[1] = a.y; Xt[2] = b.x;
+        } else {
+            const double* pt = pts + 3 * (int64_t)k;
+            Xt[0] = pt[0]; Xt[1] = pt[1]; Xt[2] = pt[2];
         }
-        double Xc[3];
-        transform(Tr + SEG_R, Tr + SEG_T, Xt, Xc);
-        const Proj p = project(Tr + SEG_Q, Xc);
-        r_out[i] = make_double2(p.u - o.x, p.v - o.y);
-        if (in < N) {   // the next observation's rows: into L1 while this one's result drains
-            const double* nr = segtab + (int64_t)s_n * SEG_STRIDE;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nr));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nr + 16));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (PTS4 ? 4 : 3) * (int64_t)k_n));
-        }
-        s = s_n; k = k_n; o = o_n;
     }
+    double Xc[3];
+    transform(T + SEG_R, T + SEG_T, Xt, Xc);
+    const Proj p = project(T + SEG_Q, Xc);
+    r_out[i] = make_double2(p.u - o.x, p.v - o.y);
 }
 
 int launch_residual(pcs_problem* p, double* r_dev)
 {
     if (p->N == 0) return PCS_OK;
-    // persistent grid: as many CTAs of 256 threads as are co-resident (one wave), capped by the observation count
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        PCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_residual<true>, 256, 0));
-        per_sm = std::max(per_sm, 1);
-    }
-    const int grid = (int)std::min<int64_t>(grid_for(p->N, 256), (int64_t)p->sm_count * per_sm);
-    PCS_CUDA(launch_pdl(k_residual<true>, dim3(grid), dim3(256), 0, p->stream, p->N, (const int32_t*)p->obs_seg,
+    PCS_CUDA(launch_pdl(k_residual<true>, dim3(grid_for(p->N, 256)), dim3(256), 0, p->stream, p->N, (const int32_t*)p->obs_seg,
                         (const int32_t*)p->key, (const double2*)p->uv, (const double*)p->segtab, (const double*)p->camtab,
                         (const double*)p->tmpl4, (double2*)r_dev));
     ++p->n_launches;
