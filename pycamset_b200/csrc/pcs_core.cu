@@ -204,11 +204,9 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p)
 // One thread per observation (a persistent, software-pipelined variant -- next observation's stream entries in registers,
 // its rows prefetched into L1 -- was measured at 67 us against 32 us: 60 registers, half the resident warps, L1 hit rate
 // down to 50 %; not kept).
-template <bool PTS4>
 __global__ void __launch_bounds__(256)
 k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __restrict__ key, const double2* __restrict__ uv,
-           const double* __restrict__ segtab, const double* __restrict__ camtab, const double* __restrict__ pts,
-           double2* __restrict__ r_out)
+           const double* __restrict__ segtab, const double* __restrict__ pts4, double2* __restrict__ r_out)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -221,14 +219,9 @@ k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __rest
         const double2* row = reinterpret_cast<const double2*>(segtab + (int64_t)s * SEG_STRIDE);
 #pragma unroll
         for (int j = 0; j < SEG_STRIDE / 2; ++j) { const double2 v = row[j]; T[2 * j] = v.x; T[2 * j + 1] = v.y; }
-        if (PTS4) {   // rows padded to 4 doubles
-            const double2* x2 = reinterpret_cast<const double2*>(pts + 4 * (int64_t)k);
-            const double2 a = x2[0], b = x2[1];
-            Xt[0] = a.x; Xt[1] = a.y; Xt[2] = b.x;
-        } else {
-            const double* pt = pts + 3 * (int64_t)k;
-            Xt[0] = pt[0]; Xt[1] = pt[1]; Xt[2] = pt[2];
-        }
+        const double2* x2 = reinterpret_cast<const double2*>(pts4 + 4 * (int64_t)k);   // point rows are padded to 4 doubles
+        const double2 a = x2[0], b = x2[1];
+        Xt[0] = a.x; Xt[1] = a.y; Xt[2] = b.x;
     }
     double Xc[3];
     transform(T + SEG_R, T + SEG_T, Xt, Xc);
@@ -239,9 +232,9 @@ k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __rest
 int launch_residual(pcs_problem* p, double* r_dev)
 {
     if (p->N == 0) return PCS_OK;
-    PCS_CUDA(launch_pdl(k_residual<true>, dim3(grid_for(p->N, 256)), dim3(256), 0, p->stream, p->N, (const int32_t*)p->obs_seg,
-                        (const int32_t*)p->key, (const double2*)p->uv, (const double*)p->segtab, (const double*)p->camtab,
-                        (const double*)p->tmpl4, (double2*)r_dev));
+    PCS_CUDA(launch_pdl(k_residual, dim3(grid_for(p->N, 256)), dim3(256), 0, p->stream, p->N, (const int32_t*)p->obs_seg,
+                        (const int32_t*)p->key, (const double2*)p->uv, (const double*)p->segtab, (const double*)p->tmpl4,
+                        (double2*)r_dev));
     ++p->n_launches;
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;

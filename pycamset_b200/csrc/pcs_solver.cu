@@ -41,7 +41,6 @@ struct LmWorkspace {
     double* Z = nullptr;     // [np][nc] column-major (nc rows): W L^-T scattered by (camera, pose)
     double* red = nullptr;   // [S nc*nc | rhs nc | gc nc | cost 1]  (all-reduce unit)
     int64_t red_doubles = 0;
-    double* t = nullptr;     // [np] Z^T delta_c
     double* delta = nullptr; // [Lparams]
     double* backup = nullptr;// [Lparams]
     double* scal = nullptr;  // [8] device scalars: pred, |dx|^2, |x|^2, ginf, cost_trial, flag
@@ -530,7 +529,7 @@ void lm_free(pcs_problem* p)
     if (w->ne_alt && w->ne_orig && p->ne == w->ne_alt) swap_normal_buffers(p, w);
     if (w->blas) cublasDestroy(w->blas);
     if (w->solver) cusolverDnDestroy(w->solver);
-    double* ptrs[] = {w->L, w->y, w->Z, w->red, w->t, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs, w->Ldiag, w->ne_alt};
+    double* ptrs[] = {w->L, w->y, w->Z, w->red, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs, w->Ldiag, w->ne_alt};
     for (double* q : ptrs) if (q) cudaFree(q);
     if (w->info) cudaFree(w->info);
     if (w->bar) cudaFree(w->bar);
@@ -595,7 +594,6 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
         w->np = 6 * (int64_t)p->M;
         PCS_CUDA(cudaMalloc((void**)&w->L, (size_t)p->M * 36 * 8));
         PCS_CUDA(cudaMalloc((void**)&w->y, (size_t)w->np * 8));
-        PCS_CUDA(cudaMalloc((void**)&w->t, (size_t)w->np * 8));
         PCS_CUDA(cudaMalloc((void**)&w->Z, (size_t)(w->nc * w->np) * 8));
         PCS_CUDA(cudaMemsetAsync(w->Z, 0, (size_t)(w->nc * w->np) * 8, p->stream));  // sparsity pattern is static
         w->red_doubles = w->nc * w->nc + 2 * w->nc + 1;
