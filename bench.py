@@ -237,7 +237,7 @@ def workload_config(args, world, workload=None):
                     f"distortion, template chain (P=21)",
         "n_cams": n_cams, "n_poses_total": total, "poses_per_gpu": -(-total // world),
         "detect_prob": detect_prob, "sharding": f"by pose, {world} rank(s)", "seed": args.seed,
-        "l2": "flushed between timed steps (256 MiB write)",
+        "l2": "flushed between timed steps (256 MiB write)" + ("; ranks re-aligned after the flush by an untimed NCCL all-reduce" if world > 1 else ""),
     }
 
 
@@ -498,6 +498,17 @@ def measure_workload(args, workload, rank, world, dev, stream, flush_buf, steps,
         prob.normal_equations_device(x_dev.data_ptr())
         exch()
 
+    # N > 1: the untimed L2 flush before every step takes a slightly different time on every rank; without re-alignment
+    # that jitter would be charged to the step (the exchange makes the early ranks wait for the late ones).  A tiny NCCL
+    # all-reduce enqueued on the stream after the flush and BEFORE the start event lines the ranks up again; it is not
+    # inside any timed interval.
+    align_buf = torch.zeros(1, device=f"cuda:{dev}") if world > 1 else None
+
+    def flush_and_align():
+        flush_buf.zero_()
+        if world > 1:
+            dist.all_reduce(align_buf)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -518,7 +529,7 @@ def measure_workload(args, workload, rank, world, dev, stream, flush_buf, steps,
         launches0 = prob.launch_count()
         t_wall = time.perf_counter()
         for k in range(steps):
-            flush_buf.zero_()                 # L2 flush, outside the per-step event pair
+            flush_and_align()                 # L2 flush (+ rank alignment), outside the per-step event pair
             starts[k].record(stream)
             step()
             ends[k].record(stream)
@@ -561,7 +572,7 @@ def measure_workload(args, workload, rank, world, dev, stream, flush_buf, steps,
             barrier()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
             for e0, e1 in ev:
-                flush_buf.zero_(); e0.record(stream); step(); e1.record(stream)
+                flush_and_align(); e0.record(stream); step(); e1.record(stream)
             barrier()
             prob.timing_enable(True)
             for _ in range(n_steps):

@@ -59,9 +59,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Shared-memory tiles are COLUMN-major, S[c * TP + r] = element (r, c): that is the layout of the matrix in global
 // memory, so a full tile moves with 16-byte asynchronous copies (two rows of one column per copy) and a factored
@@ -309,10 +306,7 @@ k_chol_solve(CholProblem P)
     double* T = Pk + TILE_DOUBLES;             // the tile being processed
     double* X = T + TILE_DOUBLES;              // L_{i,k-1}
     double* Y = X + TILE_DOUBLES;              // L_{j,k-1}
-    double* T2 = Y + TILE_DOUBLES;             // second operand set of the trailing-tile loop (software pipeline)
-    double* X2 = T2 + TILE_DOUBLES;
-    double* Y2 = X2 + TILE_DOUBLES;
-    double* invd = Y2 + TILE_DOUBLES;          // [32]
+    double* invd = Y + TILE_DOUBLES;           // [32]
     double* colbuf = invd + TB;                // [2][32]
     double* yv = colbuf + 2 * TB;              // [nb * 32] back substitution (CTA 0)
     double* RB = yv + P.nb * TB;               // [(nb - 1) * 32][RB_STRIDE] row block of L (CTA 0)
@@ -365,42 +359,22 @@ k_chol_solve(CholProblem P)
             trace_stamp(P, k, 2);
             trace_stamp(P, k, 6);
         }
-        // Remaining tiles of the phase (large systems: ~(nb - k)^2 / 2 tiles over the grid).  Two operand sets: the copies
-        // of tile t + grid are in flight while tile t is updated and stored -- a tile visit is bound by the latency of its
-        // three 8 KB fetches from L2, not by the 32 x 32 x 32 update (trace at n = 1920: 2.9 us per visit unpipelined).
-        {
-            double* Ts[2] = {T, T2};
-            double* Xs[2] = {X, X2};
-            double* Ys[2] = {Y, Y2};
-            int bis[2], bjs[2];
-            auto issue = [&](int t, int sidx) {
-                phase_tile(k, nb, t, bis[sidx], bjs[sidx]);
-                const bool pnl = bjs[sidx] == k;   // only when the grid is narrower than the panel
-                tile_fetch(P, bis[sidx], bjs[sidx], Ts[sidx]);
-                if (k > 0) { tile_fetch(P, bis[sidx], k - 1, Xs[sidx]); if (!pnl) tile_fetch(P, bjs[sidx], k - 1, Ys[sidx]); }
-                cp_async_commit();
-            };
-            int cur = 0;
-            if (t_next < n_tiles) issue(t_next, 0);
-            for (int t = t_next; t < n_tiles; t += gridDim.x) {
-                const int tn = t + gridDim.x;
-                if (tn < n_tiles) issue(tn, cur ^ 1); else cp_async_commit();   // (empty group keeps the wait count uniform)
-                cp_async_wait_group<1>();
-                __syncthreads();
-                const int bi = bis[cur], bj = bjs[cur];
-                const bool panel = bj == k;
-                double* Tc = Ts[cur];
-                if (k > 0) tile_update<0, CH_WARPS>(Tc, Xs[cur], panel ? Pk : Ys[cur]);
-                __syncthreads();
-                if (panel) {
-                    if (warp == 0) tile_trsm(Tc, D, invd, lane);
-                    __syncthreads();
-                }
-                tile_store(P, bi, bj, Tc);
-                __syncthreads();
-                cur ^= 1;
-            }
+        for (int t = t_next; t < n_tiles; t += gridDim.x) {
+            int bi, bj;
+            phase_tile(k, nb, t, bi, bj);
+            const bool panel = bj == k;   // only when the grid is narrower than the panel
+            tile_fetch(P, bi, bj, T);
+            if (k > 0) { tile_fetch(P, bi, k - 1, X); if (!panel) tile_fetch(P, bj, k - 1, Y); }
             cp_async_wait_all();
+            __syncthreads();
+            if (k > 0) tile_update<0, CH_WARPS>(T, X, panel ? Pk : Y);
+            __syncthreads();
+            if (panel) {
+                if (warp == 0) tile_trsm(T, D, invd, lane);
+                __syncthreads();
+            }
+            tile_store(P, bi, bj, T);
+            __syncthreads();
         }
         trace_stamp(P, k, 3);
         grid_barrier(P.bar, P.bar_base + (unsigned long long)(k + 1) * gridDim.x, P.info);
@@ -517,14 +491,14 @@ k_chol_solve(CholProblem P)
 
 size_t chol_smem_bytes(int nb, int rb_cols)
 {
-    return (size_t)(8 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)rb_cols * RB_STRIDE) * sizeof(double);
+    return (size_t)(5 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)rb_cols * RB_STRIDE) * sizeof(double);
 }
 
 // capacity of the row-block buffer: the whole longest row block when it fits the opt-in shared memory, else what fits
 int chol_rb_cols(int nb, int max_optin_bytes)
 {
     const int want = std::max(nb - 1, 0) * TB;
-    const long long fixed = (long long)(8 * TILE_DOUBLES + 3 * TB + nb * TB) * (long long)sizeof(double) + 1024;
+    const long long fixed = (long long)(5 * TILE_DOUBLES + 3 * TB + nb * TB) * (long long)sizeof(double) + 1024;
     const long long room = ((long long)max_optin_bytes - fixed) / (long long)(RB_STRIDE * sizeof(double));
     const int cap = (int)std::max<long long>(0, room / TB * TB);
     return std::min(want, cap);
