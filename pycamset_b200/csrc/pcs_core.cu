@@ -201,9 +201,13 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p)
     return v;
 }
 
-// One thread per observation (a persistent, software-pipelined variant -- next observation's stream entries in registers,
-// its rows prefetched into L1 -- was measured at 67 us against 32 us: 60 registers, half the resident warps, L1 hit rate
-// down to 50 %; not kept).
+// One thread per observation.  Measured alternatives, none faster than this kernel's 32 us at 2.59 M observations
+// (profiles/r2_kres_variants.txt): a persistent, software-pipelined variant (67 us: 60 registers, half the resident warps);
+// a per-warp row cache in shared memory for (camera, pose)-sorted tables (33-34 us: L1 data-pipe wavefronts 65 -> 59 %,
+// time unchanged -- a broadcast shared load still has to deliver 16 bytes to every lane); 2 / 4 observations per thread
+// with all stream loads issued up front (33 / 35 us at 44 % / 34 % occupancy).  The time does not move with occupancy,
+// memory-level parallelism or the wavefront count: what is constant across the variants is the number of bytes each lane
+// receives through the load / store unit (232 B of rows and stream + 16 B stored per observation).
 __global__ void __launch_bounds__(256)
 k_residual(int64_t N, const int32_t* __restrict__ obs_seg, const int32_t* __restrict__ key, const double2* __restrict__ uv,
            const double* __restrict__ segtab, const double* __restrict__ pts4, double2* __restrict__ r_out)

@@ -229,20 +229,42 @@ __device__ __forceinline__ void flush_camera(int lane, int c, const double* __re
 
 // One k-step (2 observations = 4 staged rows) of the Gram update.  MASKED: rows of observations outside [a, b)
 // (a neighbouring piece sharing the step, or stale rows past the batch) contribute zero.
-template <bool MASKED>
+template <int KO>
+__device__ __forceinline__ void gram_mma(NeAcc& S, double v0, double v1)
+{
+    if constexpr (KO & 1) {
+        asm volatile("" ::"d"(v0), "d"(v1));
+    } else {
+        dmma884(S.aa[0], S.aa[1], v0, v0);
+        dmma884(S.ab[0], S.ab[1], v0, v1);
+        dmma884(S.bb[0], S.bb[1], v1, v1);
+    }
+}
+template <int KO>
+__device__ __forceinline__ void gram_load(const double* __restrict__ f, double& v0, double& v1)
+{
+    if constexpr (KO & 2) {
+        v0 = __longlong_as_double((long long)(size_t)f);   // address-dependent bits: nothing is loaded
+        v1 = v0 * 0.5;
+    } else {
+        v0 = f[0];
+        v1 = f[NE_TILE_DOUBLES];
+    }
+}
+
+template <bool MASKED, int KO = 0>
 __device__ __forceinline__ void gram_step(NeAcc& S, const double* __restrict__ ws, int ld_L, int ks, int jb, int a, int b)
 {
     const double* f = ws + 32 * ks + (ld_L ^ (((ks & 1) << 3) | (ks & 2)));
-    double v0 = f[0], v1 = f[NE_TILE_DOUBLES];
+    double v0, v1;
+    gram_load<KO>(f, v0, v1);
     if (MASKED) {
         const int ob = 2 * ks + jb;
         const bool ok = ob >= a && ob < b;
         v0 = ok ? v0 : 0.0;
         v1 = ok ? v1 : 0.0;
     }
-    dmma884(S.aa[0], S.aa[1], v0, v0);
-    dmma884(S.ab[0], S.ab[1], v0, v1);
-    dmma884(S.bb[0], S.bb[1], v1, v1);
+    gram_mma<KO>(S, v0, v1);
 }
 
 // Streamed observation loads: every observation is read exactly once per evaluation, so the loads bypass L1
@@ -278,6 +300,7 @@ __device__ __forceinline__ void load_obs(NeObs& o, int64_t i, int64_t end, const
 struct NeRows {
     double xD, yD, Au[5], Av[5], Pm[6], Wc[6], res[2];
 };
+template <bool FAKE_ROWS = false>
 __device__ __forceinline__ void eval_rows(const NeObs& o, const double* __restrict__ camtab, const double* __restrict__ posetab,
                                           const double* __restrict__ pts, NeRows& R)
 {
@@ -285,7 +308,7 @@ __device__ __forceinline__ void eval_rows(const NeObs& o, const double* __restri
     const double* ct = camtab + (int64_t)max(o.c, 0) * CAM_STRIDE;
     const double* ptab = posetab + (int64_t)max(o.m, 0) * POSE_STRIDE;
     ObsJacCam J;
-    eval_obs_cam(ct, ptab, pts + 4 * (int64_t)(o.c < 0 ? 0 : o.k), o.uv.x, o.uv.y, R.res, J);
+    eval_obs_cam<FAKE_ROWS>(ct, ptab, pts + 4 * (int64_t)(o.c < 0 ? 0 : o.k), o.uv.x, o.uv.y, R.res, J);
     R.xD = J.xD; R.yD = J.yD;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { R.Au[i] = J.Au[i]; R.Av[i] = J.Av[i]; }
@@ -309,7 +332,10 @@ __device__ __forceinline__ void stage_rows(const NeRows& R, double* __restrict__
 // OPL = observations per lane and loop trip.  With OPL = 2 a lane evaluates two observations back to back (two
 // independent dependency chains: the evaluation phase is latency-bound, not issue-bound) and the warp then runs the
 // staging + Gram phase once per half, re-using the one 8 KB staging buffer.
-template <int CTAS_PER_SM, int WARPS, int OPL>
+// KO: knock-out bits of the attribution experiment (tools/kne_knockout.sh, built with -DPCS_NE_KNOCKOUT only; results are
+// wrong by construction, only the time is read): 1 = no DMMA in the Gram loop, 2 = no fragment loads, 4 = no staging
+// stores, 8 = table rows made up from registers (no row loads), 16 = no segment flush.
+template <int CTAS_PER_SM, int WARPS, int OPL, int KO = 0>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
 k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_pose,
          const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv, const int64_t* __restrict__ seg_start,
@@ -361,7 +387,7 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
 #pragma unroll
         for (int h = 0; h < OPL; ++h) load_obs(nxt[h], base + 32 * (OPL + h) + lane, end, s_cam, s_pose, s_key, s_uv);
 #pragma unroll
-        for (int h = 0; h < OPL; ++h) eval_rows(ob[h], camtab, posetab, pts, rows[h]);
+        for (int h = 0; h < OPL; ++h) eval_rows<(KO & 8) != 0>(ob[h], camtab, posetab, pts, rows[h]);
         // the next trip's pose rows (new for every segment) are pulled into L1 while this trip's Gram phases run
 #pragma unroll
         for (int h = 0; h < OPL; ++h)
@@ -376,8 +402,17 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
             if (cnt <= 0) break;
             const int c = (OPL > 1 && h) ? ob[OPL - 1].c : ob[0].c, m = (OPL > 1 && h) ? ob[OPL - 1].m : ob[0].m;
             if (lane < cnt) {
-                if (OPL > 1 && h) stage_rows(rows[OPL - 1], st_u, st_v, st_rot);
-                else stage_rows(rows[0], st_u, st_v, st_rot);
+                if constexpr (KO & 4) {
+                    const NeRows& Rr = rows[0];
+                    asm volatile("" ::"d"(Rr.xD), "d"(Rr.yD), "d"(Rr.res[0]), "d"(Rr.res[1]));
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) asm volatile("" ::"d"(Rr.Au[q]), "d"(Rr.Av[q]));
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) asm volatile("" ::"d"(Rr.Pm[q]), "d"(Rr.Wc[q]));
+                } else {
+                    if (OPL > 1 && h) stage_rows(rows[OPL - 1], st_u, st_v, st_rot);
+                    else stage_rows(rows[0], st_u, st_v, st_rot);
+                }
             }
             // piece heads: lanes whose (camera, pose) differs from the previous observation's
             int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
@@ -392,7 +427,10 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
                 pieces &= pieces - 1;
                 const int b = pieces ? __ffs(pieces) - 1 : cnt;
                 if ((heads >> a) & 1u) {
-                    if (cur_c >= 0) flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
+                    if (cur_c >= 0) {
+                        if constexpr (KO & 16) { asm volatile("" ::"d"(S.aa[0]), "d"(S.aa[1]), "d"(S.ab[0]), "d"(S.ab[1]), "d"(S.bb[0]), "d"(S.bb[1])); acc_zero(S); }
+                        else flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
+                    }
                     const int nc = __shfl_sync(0xffffffffu, c, a);
                     if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
                     ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
@@ -402,7 +440,7 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
                 int ks = a >> 1;
                 const int k1 = (b - 1) >> 1;
                 if (a & 1) {
-                    gram_step<true>(S, ws, ld_L, ks, jb, a, b);
+                    gram_step<true, KO>(S, ws, ld_L, ks, jb, a, b);
                     ++ks;
                 }
                 const int k_full = (b & 1) ? k1 : k1 + 1;   // first step that needs the tail mask (or one past the end)
@@ -411,18 +449,13 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const double* f = ws + 32 * (ks + u) + (ld_L ^ ((((ks + u) & 1) << 3) | ((ks + u) & 2)));
-                        v0[u] = f[0];
-                        v1[u] = f[NE_TILE_DOUBLES];
+                        gram_load<KO>(f, v0[u], v1[u]);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        dmma884(S.aa[0], S.aa[1], v0[u], v0[u]);
-                        dmma884(S.ab[0], S.ab[1], v0[u], v1[u]);
-                        dmma884(S.bb[0], S.bb[1], v1[u], v1[u]);
-                    }
+                    for (int u = 0; u < 4; ++u) gram_mma<KO>(S, v0[u], v1[u]);
                 }
-                for (; ks < k_full; ++ks) gram_step<false>(S, ws, ld_L, ks, jb, a, b);
-                if (ks <= k1) gram_step<true>(S, ws, ld_L, ks, jb, a, b);
+                for (; ks < k_full; ++ks) gram_step<false, KO>(S, ws, ld_L, ks, jb, a, b);
+                if (ks <= k1) gram_step<true, KO>(S, ws, ld_L, ks, jb, a, b);
             }
             __syncwarp();
         }
@@ -760,8 +793,27 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
     const int64_t* ranges = p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1);
+    auto kern_fp64 = k_normal<5, 4, 1>;
+#ifdef PCS_NE_KNOCKOUT
+    {
+        static const int ko = [] { const char* e = std::getenv("PCS_NE_KO"); return e ? std::atoi(e) : 0; }();
+        switch (ko) {
+            case 1: kern_fp64 = k_normal<5, 4, 1, 1>; break;
+            case 2: kern_fp64 = k_normal<5, 4, 1, 2>; break;
+            case 3: kern_fp64 = k_normal<5, 4, 1, 3>; break;
+            case 4: kern_fp64 = k_normal<5, 4, 1, 4>; break;
+            case 7: kern_fp64 = k_normal<5, 4, 1, 7>; break;
+            case 8: kern_fp64 = k_normal<5, 4, 1, 8>; break;
+            case 16: kern_fp64 = k_normal<5, 4, 1, 16>; break;
+            case 23: kern_fp64 = k_normal<5, 4, 1, 23>; break;
+            case 31: kern_fp64 = k_normal<5, 4, 1, 31>; break;
+            default: break;
+        }
+        if (ko) PCS_CUDA(ensure_dynamic_smem(kern_fp64, smem));
+    }
+#endif
     // programmatic dependent launch: the grid becomes resident while k_prepare_tables drains (pdl_wait inside the kernel)
-    PCS_CUDA(launch_pdl(mixed ? kern_mixed : k_normal<5, 4, 1>, dim3(grid), dim3(warps * 32), smem, p->stream, (int)n_warps, ranges,
+    PCS_CUDA(launch_pdl(mixed ? kern_mixed : kern_fp64, dim3(grid), dim3(warps * 32), smem, p->stream, (int)n_warps, ranges,
                         (const int32_t*)p->s_cam, (const int32_t*)p->s_pose, (const int32_t*)p->s_key, (const double2*)p->s_uv,
                         (const int64_t*)p->seg_start, (const double*)p->camtab, (const double*)p->posetab, (const double*)p->tmpl4,
                         p->U, p->gc, p->cost, p->V, p->gp, p->W));
