@@ -56,16 +56,6 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 __device__ __forceinline__ int stage_row(int o, int r) { return (2 * o + (r ^ ((o >> 1) & 1))) * 8; }
 __device__ __forceinline__ int stage_rot(int o) { return 4 * (o & 1) + 2 * ((o >> 2) & 1); }
 
-__device__ __forceinline__ void stage_store_row(double* __restrict__ row, int rot, const double t0[8], const double t1[8])
-{
-#pragma unroll
-    for (int c = 0; c < 8; c += 2) {
-        const int pos = c ^ rot;
-        *reinterpret_cast<double2*>(row + pos) = make_double2(t0[c], t0[c + 1]);
-        *reinterpret_cast<double2*>(row + NE_TILE_DOUBLES + pos) = make_double2(t1[c], t1[c + 1]);
-    }
-}
-
 // Fragment (m8n8 accumulator) layout: lane holds rows lane >> 2, columns 2 (lane & 3) + {0, 1} of an 8 x 8 tile.
 // Column order of the 16 accumulated columns: 0..14 = camera (9 intrinsic, 3 rotation (tangent), 3 translation), 15 = r.
 struct NeAcc {
@@ -227,8 +217,8 @@ __device__ __forceinline__ void flush_camera(int lane, int c, const double* __re
     __syncwarp();
 }
 
-// One k-step (2 observations = 4 staged rows) of the Gram update.  MASKED: rows of observations outside [a, b)
-// (a neighbouring piece sharing the step, or stale rows past the batch) contribute zero.
+// One k-step (2 observations = 4 staged rows) of the Gram update: fragment loads and the three DMMA (the knock-out
+// variants of the attribution experiment replace either by a no-op that keeps the operands alive).
 template <int KO>
 __device__ __forceinline__ void gram_mma(NeAcc& S, double v0, double v1)
 {
@@ -250,21 +240,6 @@ __device__ __forceinline__ void gram_load(const double* __restrict__ f, double& 
         v0 = f[0];
         v1 = f[NE_TILE_DOUBLES];
     }
-}
-
-template <bool MASKED, int KO = 0>
-__device__ __forceinline__ void gram_step(NeAcc& S, const double* __restrict__ ws, int ld_L, int ks, int jb, int a, int b)
-{
-    const double* f = ws + 32 * ks + (ld_L ^ (((ks & 1) << 3) | (ks & 2)));
-    double v0, v1;
-    gram_load<KO>(f, v0, v1);
-    if (MASKED) {
-        const int ob = 2 * ks + jb;
-        const bool ok = ob >= a && ob < b;
-        v0 = ok ? v0 : 0.0;
-        v1 = ok ? v1 : 0.0;
-    }
-    gram_mma<KO>(S, v0, v1);
 }
 
 // Streamed observation loads: every observation is read exactly once per evaluation, so the loads bypass L1
@@ -315,27 +290,42 @@ __device__ __forceinline__ void eval_rows(const NeObs& o, const double* __restri
 #pragma unroll
     for (int i = 0; i < 6; ++i) { R.Pm[i] = J.Pm[i]; R.Wc[i] = J.Wc[i]; }
 }
+// The first tile of a staged row pair is [xD 1 0 0 | Au0..3] / [0 0 yD 1 | Av0..3]: six of its sixteen entries are the
+// constants 1 / 0.  Every lane always writes the same slot, so they are written once per kernel (stage_constants) and the
+// per-observation staging is 12 sixteen-byte + 2 eight-byte stores instead of 16 sixteen-byte ones.
+__device__ __forceinline__ void stage_constants(double* __restrict__ st_u, double* __restrict__ st_v, int st_rot)
+{
+    st_u[(0 ^ st_rot) + 1] = 1.0;
+    *reinterpret_cast<double2*>(st_u + (2 ^ st_rot)) = make_double2(0.0, 0.0);
+    *reinterpret_cast<double2*>(st_v + (0 ^ st_rot)) = make_double2(0.0, 0.0);
+    st_v[(2 ^ st_rot) + 1] = 1.0;
+}
 __device__ __forceinline__ void stage_rows(const NeRows& R, double* __restrict__ st_u, double* __restrict__ st_v, int st_rot)
 {
+    st_u[0 ^ st_rot] = R.xD;
+    st_v[2 ^ st_rot] = R.yD;
+    *reinterpret_cast<double2*>(st_u + (4 ^ st_rot)) = make_double2(R.Au[0], R.Au[1]);
+    *reinterpret_cast<double2*>(st_u + (6 ^ st_rot)) = make_double2(R.Au[2], R.Au[3]);
+    *reinterpret_cast<double2*>(st_v + (4 ^ st_rot)) = make_double2(R.Av[0], R.Av[1]);
+    *reinterpret_cast<double2*>(st_v + (6 ^ st_rot)) = make_double2(R.Av[2], R.Av[3]);
     {
-        const double t0[8] = {R.xD, 1.0, 0.0, 0.0, R.Au[0], R.Au[1], R.Au[2], R.Au[3]};
         const double t1[8] = {R.Au[4], R.Wc[0], R.Wc[1], R.Wc[2], R.Pm[0], R.Pm[1], R.Pm[2], R.res[0]};
-        stage_store_row(st_u, st_rot, t0, t1);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(st_u + NE_TILE_DOUBLES + (c ^ st_rot)) = make_double2(t1[c], t1[c + 1]);
     }
     {
-        const double t0[8] = {0.0, 0.0, R.yD, 1.0, R.Av[0], R.Av[1], R.Av[2], R.Av[3]};
         const double t1[8] = {R.Av[4], R.Wc[3], R.Wc[4], R.Wc[5], R.Pm[3], R.Pm[4], R.Pm[5], R.res[1]};
-        stage_store_row(st_v, st_rot, t0, t1);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(st_v + NE_TILE_DOUBLES + (c ^ st_rot)) = make_double2(t1[c], t1[c + 1]);
     }
 }
 
-// OPL = observations per lane and loop trip.  With OPL = 2 a lane evaluates two observations back to back (two
-// independent dependency chains: the evaluation phase is latency-bound, not issue-bound) and the warp then runs the
-// staging + Gram phase once per half, re-using the one 8 KB staging buffer.
 // KO: knock-out bits of the attribution experiment (tools/kne_knockout.sh, built with -DPCS_NE_KNOCKOUT only; results are
 // wrong by construction, only the time is read): 1 = no DMMA in the Gram loop, 2 = no fragment loads, 4 = no staging
 // stores, 8 = table rows made up from registers (no row loads), 16 = no segment flush.
-template <int CTAS_PER_SM, int WARPS, int OPL, int KO = 0>
+// (A variant with two observations per lane and loop trip -- two independent evaluation chains -- was measured at 0.177 ms
+// against 0.135 ms: the second observation's rows spill.  Removed.)
+template <int CTAS_PER_SM, int WARPS, int KO = 0>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
 k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_pose,
          const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv, const int64_t* __restrict__ seg_start,
@@ -362,7 +352,6 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     scratch[lane] = 0.0;
     scratch[32 + lane] = lane == 30 ? 1.0 : 0.0;       // Tbar[7][6] = 1
     for (int e = lane; e < 192; e += 32) scratch[64 + e] = 0.0;
-    __syncwarp();
     int64_t cur_seg = sb - 1;   // segments are visited in order: a piece head advances this counter
     int cur_c = -1, cur_m = -1;
     int last_c = -1, last_m = -1;  // (camera, pose) of the last observation of the previous batch
@@ -371,94 +360,100 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     double* const st_u = ws + stage_row(lane, 0);
     double* const st_v = ws + stage_row(lane, 1);
     const int st_rot = stage_rot(lane);
+    stage_constants(st_u, st_v, st_rot);   // the 1 / 0 entries of the first tile never change: written once
+    __syncwarp();
     const int g8 = lane >> 2, jb = (lane >> 1) & 1, jr = lane & 1;
     const int ld_L = 16 * jb + 8 * jr + (g8 ^ (4 * jb));
+    // fragment address of k-step ks: ws + 32 ks + (ld_L ^ X(ks)), X(ks) = 8 bit0(ks) + 2 bit1(ks): four lane constants,
+    // the rest of the address is a compile-time offset of the unrolled step
+    const double* const fb0 = ws + ld_L;
+    const double* const fb1 = ws + (ld_L ^ 8);
+    const double* const fb2 = ws + (ld_L ^ 2);
+    const double* const fb3 = ws + (ld_L ^ 10);
 
     // software prefetch: the inputs of the next trip are requested before the current trip is evaluated
-    NeObs nxt[OPL];
-#pragma unroll
-    for (int h = 0; h < OPL; ++h) load_obs(nxt[h], begin + 32 * h + lane, end, s_cam, s_pose, s_key, s_uv);
+    NeObs nxt;
+    load_obs(nxt, begin + lane, end, s_cam, s_pose, s_key, s_uv);
 
-    for (int64_t base = begin; base < end; base += 32 * OPL) {
-        NeObs ob[OPL];
-        NeRows rows[OPL];
+    for (int64_t base = begin; base < end; base += 32) {
+        const NeObs ob = nxt;
+        NeRows rows;
+        load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);
+        eval_rows<(KO & 8) != 0>(ob, camtab, posetab, pts, rows);
+        // the next trip's pose rows (new for every segment) are pulled into L1 while this trip's Gram phase runs
+        if (nxt.m >= 0) {
+            const double* nx = posetab + (int64_t)nxt.m * POSE_STRIDE;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
+        }
+        const int cnt = (int)min((int64_t)32, end - base);
+        const int c = ob.c, m = ob.m;
+        if (lane < cnt) {
+            if constexpr (KO & 4) {
+                asm volatile("" ::"d"(rows.xD), "d"(rows.yD), "d"(rows.res[0]), "d"(rows.res[1]));
 #pragma unroll
-        for (int h = 0; h < OPL; ++h) ob[h] = nxt[h];
+                for (int q = 0; q < 5; ++q) asm volatile("" ::"d"(rows.Au[q]), "d"(rows.Av[q]));
 #pragma unroll
-        for (int h = 0; h < OPL; ++h) load_obs(nxt[h], base + 32 * (OPL + h) + lane, end, s_cam, s_pose, s_key, s_uv);
-#pragma unroll
-        for (int h = 0; h < OPL; ++h) eval_rows<(KO & 8) != 0>(ob[h], camtab, posetab, pts, rows[h]);
-        // the next trip's pose rows (new for every segment) are pulled into L1 while this trip's Gram phases run
-#pragma unroll
-        for (int h = 0; h < OPL; ++h)
-            if (nxt[h].m >= 0) {
-                const double* nx = posetab + (int64_t)nxt[h].m * POSE_STRIDE;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
+                for (int q = 0; q < 6; ++q) asm volatile("" ::"d"(rows.Pm[q]), "d"(rows.Wc[q]));
+            } else {
+                stage_rows(rows, st_u, st_v, st_rot);
             }
-#pragma unroll 1
-        for (int h = 0; h < OPL; ++h) {
-            const int cnt = (int)min((int64_t)32, end - base - 32 * h);
-            if (cnt <= 0) break;
-            const int c = (OPL > 1 && h) ? ob[OPL - 1].c : ob[0].c, m = (OPL > 1 && h) ? ob[OPL - 1].m : ob[0].m;
-            if (lane < cnt) {
-                if constexpr (KO & 4) {
-                    const NeRows& Rr = rows[0];
-                    asm volatile("" ::"d"(Rr.xD), "d"(Rr.yD), "d"(Rr.res[0]), "d"(Rr.res[1]));
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) asm volatile("" ::"d"(Rr.Au[q]), "d"(Rr.Av[q]));
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) asm volatile("" ::"d"(Rr.Pm[q]), "d"(Rr.Wc[q]));
-                } else {
-                    if (OPL > 1 && h) stage_rows(rows[OPL - 1], st_u, st_v, st_rot);
-                    else stage_rows(rows[0], st_u, st_v, st_rot);
+        }
+        // piece heads: lanes whose (camera, pose) differs from the previous observation's
+        int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
+        if (lane == 0) { pc = last_c; pm = last_m; }
+        const unsigned heads = __ballot_sync(0xffffffffu, lane < cnt && (c != pc || m != pm));
+        last_c = __shfl_sync(0xffffffffu, c, cnt - 1);
+        last_m = __shfl_sync(0xffffffffu, m, cnt - 1);
+        __syncwarp();
+        unsigned pieces = heads | 1u;  // a batch may start in the middle of a segment
+        while (pieces) {
+            const int a = __ffs(pieces) - 1;
+            pieces &= pieces - 1;
+            const int b = pieces ? __ffs(pieces) - 1 : cnt;
+            if ((heads >> a) & 1u) {
+                if (cur_c >= 0) {
+                    if constexpr (KO & 16) { asm volatile("" ::"d"(S.aa[0]), "d"(S.aa[1]), "d"(S.ab[0]), "d"(S.ab[1]), "d"(S.bb[0]), "d"(S.bb[1])); acc_zero(S); }
+                    else flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
                 }
+                const int nc = __shfl_sync(0xffffffffu, c, a);
+                if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
+                ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
             }
-            // piece heads: lanes whose (camera, pose) differs from the previous observation's
-            int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
-            if (lane == 0) { pc = last_c; pm = last_m; }
-            const unsigned heads = __ballot_sync(0xffffffffu, lane < cnt && (c != pc || m != pm));
-            last_c = __shfl_sync(0xffffffffu, c, cnt - 1);
-            last_m = __shfl_sync(0xffffffffu, m, cnt - 1);
-            __syncwarp();
-            unsigned pieces = heads | 1u;  // a batch may start in the middle of a segment
-            while (pieces) {
-                const int a = __ffs(pieces) - 1;
-                pieces &= pieces - 1;
-                const int b = pieces ? __ffs(pieces) - 1 : cnt;
-                if ((heads >> a) & 1u) {
-                    if (cur_c >= 0) {
-                        if constexpr (KO & 16) { asm volatile("" ::"d"(S.aa[0]), "d"(S.aa[1]), "d"(S.ab[0]), "d"(S.ab[1]), "d"(S.bb[0]), "d"(S.bb[1])); acc_zero(S); }
-                        else flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
-                    }
-                    const int nc = __shfl_sync(0xffffffffu, c, a);
-                    if (nc != cur_c && cur_c >= 0) flush_camera(lane, cur_c, camtab, scratch + 64, U, gc, cost);
-                    ++cur_seg; cur_c = nc; cur_m = __shfl_sync(0xffffffffu, m, a);
-                }
-                // k-steps of the piece: boundary steps shared with a neighbouring piece (odd a / odd b) are masked,
-                // interior steps run unmasked in groups of four with their fragment loads hoisted
-                int ks = a >> 1;
-                const int k1 = (b - 1) >> 1;
-                if (a & 1) {
-                    gram_step<true, KO>(S, ws, ld_L, ks, jb, a, b);
-                    ++ks;
-                }
-                const int k_full = (b & 1) ? k1 : k1 + 1;   // first step that needs the tail mask (or one past the end)
-                for (; ks + 4 <= k_full; ks += 4) {
+            // k-steps (2 observations each) of the piece [a, b), fully unrolled: every fragment address is a lane constant
+            // plus a compile-time offset.
+            if (a == 0 && b == 32) {
+                // the whole batch belongs to one segment (the common case): 16 unmasked steps, loads of four steps hoisted
+#pragma unroll
+                for (int k4 = 0; k4 < 16; k4 += 4) {
                     double v0[4], v1[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const double* f = ws + 32 * (ks + u) + (ld_L ^ ((((ks + u) & 1) << 3) | ((ks + u) & 2)));
-                        gram_load<KO>(f, v0[u], v1[u]);
-                    }
+                    gram_load<KO>(fb0 + 32 * k4, v0[0], v1[0]);
+                    gram_load<KO>(fb1 + 32 * (k4 + 1), v0[1], v1[1]);
+                    gram_load<KO>(fb2 + 32 * (k4 + 2), v0[2], v1[2]);
+                    gram_load<KO>(fb3 + 32 * (k4 + 3), v0[3], v1[3]);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) gram_mma<KO>(S, v0[u], v1[u]);
                 }
-                for (; ks < k_full; ++ks) gram_step<false, KO>(S, ws, ld_L, ks, jb, a, b);
-                if (ks <= k1) gram_step<true, KO>(S, ws, ld_L, ks, jb, a, b);
+            } else {
+                // general piece: steps outside [a, b) are skipped (warp-uniform), steps shared with a neighbouring piece or
+                // reaching past the end of the batch are masked per observation
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) {
+                    if (2 * ks + 2 <= a || 2 * ks >= b) continue;
+                    const double* f = ((ks & 3) == 0 ? fb0 : (ks & 3) == 1 ? fb1 : (ks & 3) == 2 ? fb2 : fb3) + 32 * ks;
+                    double v0, v1;
+                    gram_load<KO>(f, v0, v1);
+                    if (2 * ks < a || 2 * ks + 2 > b) {
+                        const int o = 2 * ks + jb;
+                        const bool ok = o >= a && o < b;
+                        v0 = ok ? v0 : 0.0;
+                        v1 = ok ? v1 : 0.0;
+                    }
+                    gram_mma<KO>(S, v0, v1);
+                }
             }
-            __syncwarp();
         }
+        __syncwarp();
     }
     if (cur_c >= 0) {
         flush_segment(S, lane, cur_seg, cur_c, cur_m, camtab, posetab, scratch, scratch + 64, V, gp, W);
@@ -783,7 +778,7 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     const size_t smem = (size_t)warps * (mixed ? NEM_WARP_DOUBLES : NE_WARP_DOUBLES) * sizeof(double);
     auto kern_mixed = nem_ctas == 5 ? k_normal_mixed<5, 4> : k_normal_mixed<4, 4>;
     if (mixed) PCS_CUDA(ensure_dynamic_smem(kern_mixed, smem));
-    else PCS_CUDA(ensure_dynamic_smem(k_normal<5, 4, 1>, smem));
+    else PCS_CUDA(ensure_dynamic_smem(k_normal<5, 4>, smem));
     // persistent-style grid: `ctas` CTAs of `warps` warps per SM; at least ~64 observations per warp
     const int64_t n_part_obs = p->N / n_parts + 1;
     int64_t n_warps = std::min<int64_t>((n_part_obs + 63) / 64, (int64_t)p->sm_count * ctas * warps);
@@ -793,20 +788,20 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
     const int64_t* ranges = p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1);
-    auto kern_fp64 = k_normal<5, 4, 1>;
+    auto kern_fp64 = k_normal<5, 4>;
 #ifdef PCS_NE_KNOCKOUT
     {
         static const int ko = [] { const char* e = std::getenv("PCS_NE_KO"); return e ? std::atoi(e) : 0; }();
         switch (ko) {
-            case 1: kern_fp64 = k_normal<5, 4, 1, 1>; break;
-            case 2: kern_fp64 = k_normal<5, 4, 1, 2>; break;
-            case 3: kern_fp64 = k_normal<5, 4, 1, 3>; break;
-            case 4: kern_fp64 = k_normal<5, 4, 1, 4>; break;
-            case 7: kern_fp64 = k_normal<5, 4, 1, 7>; break;
-            case 8: kern_fp64 = k_normal<5, 4, 1, 8>; break;
-            case 16: kern_fp64 = k_normal<5, 4, 1, 16>; break;
-            case 23: kern_fp64 = k_normal<5, 4, 1, 23>; break;
-            case 31: kern_fp64 = k_normal<5, 4, 1, 31>; break;
+            case 1: kern_fp64 = k_normal<5, 4, 1>; break;
+            case 2: kern_fp64 = k_normal<5, 4, 2>; break;
+            case 3: kern_fp64 = k_normal<5, 4, 3>; break;
+            case 4: kern_fp64 = k_normal<5, 4, 4>; break;
+            case 7: kern_fp64 = k_normal<5, 4, 7>; break;
+            case 8: kern_fp64 = k_normal<5, 4, 8>; break;
+            case 16: kern_fp64 = k_normal<5, 4, 16>; break;
+            case 23: kern_fp64 = k_normal<5, 4, 23>; break;
+            case 31: kern_fp64 = k_normal<5, 4, 31>; break;
             default: break;
         }
         if (ko) PCS_CUDA(ensure_dynamic_smem(kern_fp64, smem));
