@@ -267,7 +267,7 @@ __device__ __forceinline__ void load_obs(NeObs& o, int64_t i, int64_t end, const
                                          const double2* __restrict__ s_uv)
 {
     if (i < end) { o.c = ld_stream(s_cam + i); o.m = ld_stream(s_pose + i); o.k = ld_stream(s_key + i); o.uv = ld_stream(s_uv + i); }
-    else { o.c = -1; o.m = -1; }
+    else { o.c = -1; o.m = -1; o.k = 0; o.uv = make_double2(0.0, 0.0); }
 }
 
 // Evaluated rows of one observation, as staged: tile 0 = [xD 1 0 0 Au0..3] / [0 0 yD 1 Av0..3],
@@ -388,16 +388,16 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
         }
         const int cnt = (int)min((int64_t)32, end - base);
         const int c = ob.c, m = ob.m;
-        if (lane < cnt) {
-            if constexpr (KO & 4) {
-                asm volatile("" ::"d"(rows.xD), "d"(rows.yD), "d"(rows.res[0]), "d"(rows.res[1]));
+        // every lane stages its rows, also the lanes past the end of the range (they evaluated row 0 of every table: finite
+        // values, masked out of the Gram steps below): without a predicate the stores are free to move up into the evaluation
+        if constexpr (KO & 4) {
+            asm volatile("" ::"d"(rows.xD), "d"(rows.yD), "d"(rows.res[0]), "d"(rows.res[1]));
 #pragma unroll
-                for (int q = 0; q < 5; ++q) asm volatile("" ::"d"(rows.Au[q]), "d"(rows.Av[q]));
+            for (int q = 0; q < 5; ++q) asm volatile("" ::"d"(rows.Au[q]), "d"(rows.Av[q]));
 #pragma unroll
-                for (int q = 0; q < 6; ++q) asm volatile("" ::"d"(rows.Pm[q]), "d"(rows.Wc[q]));
-            } else {
-                stage_rows(rows, st_u, st_v, st_rot);
-            }
+            for (int q = 0; q < 6; ++q) asm volatile("" ::"d"(rows.Pm[q]), "d"(rows.Wc[q]));
+        } else {
+            stage_rows(rows, st_u, st_v, st_rot);
         }
         // piece heads: lanes whose (camera, pose) differs from the previous observation's
         int pc = __shfl_up_sync(0xffffffffu, c, 1), pm = __shfl_up_sync(0xffffffffu, m, 1);
