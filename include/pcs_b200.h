@@ -235,6 +235,14 @@ PCS_API int pcs_spd_solve(int device, int64_t n, const double* A, const double* 
  * on its own. */
 PCS_API int pcs_syrk_sub(int device, int64_t n, int64_t k, const double* Z, double* S);
 
+/* Block sparsity of the pose elimination inside pcs_lm_solve.  A camera that does not see a pose leaves a zero 15 x 6
+ * block in Z; the pattern is static, so the solver orders the pose columns by visibility pattern and visits only the
+ * (96-row tile pair, 16-column slab) units of S -= Z Z^T whose operands are both non-zero (csrc/pcs_schur.cu).
+ * *fraction = visited units / all units; 1.0 means the dense iteration space is used (pattern too dense to pay, or
+ * PCS_LM_SCHUR=dense).  Builds the solver workspace if it does not exist yet.  Diagnostic; no reference counterpart
+ * (scipy's LSMR never forms the reduced system, optimisation_handling.py:88-98). */
+PCS_API int pcs_lm_schur_fraction(pcs_problem* p, double* fraction);
+
 /* Optional kernel timing: when enabled, every launch of the fused normal-equation kernel is bracketed by a pair of
  * CUDA events on the problem's stream (a ring of 1024 pairs, so a timed loop needs no synchronisation inside).
  * pcs_timing_get returns the duration (ms) of the most recent launch, pcs_timing_get_all the durations of the last

@@ -176,8 +176,17 @@ int launch_point_blocks(pcs_problem* p);   // chain 1: Pk, gk, Xck, Ymk (targets
 inline int64_t ne_zero_doubles(const pcs_problem* p) { return p->W - p->ne; }   // everything accumulated with reductions precedes W
 int ensure_pinned(pcs_problem* p, int64_t doubles);
 void lm_free(pcs_problem* p);
-// pcs_schur.cu: S (n x n, column-major, lower) -= Z Z^T, Z column-major [k][n]
-int launch_schur_syrk(cudaStream_t st, int sm_count, int64_t n, int64_t k, const double* Z, double* S);
+// pcs_schur.cu: S (n x n, column-major, lower) -= Z Z^T, Z column-major [k][n]; with a plan only the listed non-zero
+// (tile, slab) units are visited and pose m's six columns sit at 6 pose_slot[m] .. 6 pose_slot[m] + 5
+struct SchurPlan {
+    int32_t* pose_slot = nullptr;   // [M] device, nullptr = identity
+    void* units = nullptr;          // int2[n_units] device, nullptr = dense iteration space
+    int64_t n_units = 0;
+    double fraction = 1.0;          // non-zero units / all units
+};
+int schur_plan_build(pcs_problem* p, int64_t nc, int64_t nl, SchurPlan* plan);
+void schur_plan_free(SchurPlan* plan);
+int launch_schur_syrk(cudaStream_t st, int sm_count, int64_t n, int64_t k, const double* Z, double* S, const SchurPlan* plan = nullptr);
 // pcs_chol.cu: dense SPD solve of the reduced camera system in one persistent kernel
 int chol_prepare(int device, int64_t n, double** Ldiag, unsigned long long** bar, int* grid);
 int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t ld, double* rhs, double* Ldiag,

@@ -11,7 +11,14 @@
 //     slabs; Z is column-major, so a slab row (96 consecutive matrix rows of one column) is contiguous.
 //   * 8 warps, warp tile 48 x 24 = 6 x 3 DMMA m8n8k4 accumulators; A and B fragments of a k-step are plain 8-byte
 //     loads from the slab (row stride 104 doubles: the minimum two wavefronts per load).
+//   * Block sparsity (LIST variant): a camera that does not see a pose leaves a zero 15 x 6 block in Z.  The sparsity
+//     pattern is static, so schur_plan_build() orders the pose columns by their visibility pattern (poses seen by the same
+//     row blocks become neighbours) and lists the (tile, slab) units whose two operand slabs are both non-zero; the kernel
+//     then streams that list instead of the full iteration space.  On the 32-camera ring (every pose seen by half of the
+//     cameras) 57 % of the units remain; on the dome (95 % fill) the list is not used.
 #include <algorithm>
+#include <numeric>
+#include <vector>
 
 #include "pcs_internal.cuh"
 
@@ -91,18 +98,38 @@ __device__ __forceinline__ void fetch_stage(const FetchPlan<ALIGNED>& fp, double
     }
 }
 
-template <bool ALIGNED>
+constexpr int UL_CHUNK = 64;   // LIST: unit-list entries per shared-memory chunk (two chunks resident)
+
+// LIST: the iteration space is the list `units` of non-zero (tile, slab) pairs -- entry = {ti << 16 | tj, slab}, sorted by
+// tile -- instead of all n_lower x n_slabs pairs.
+template <bool ALIGNED, bool LIST>
 __global__ void __launch_bounds__(S_THREADS, 2)
-k_schur_syrk(int64_t nc, int64_t np, const double* __restrict__ Z, double* __restrict__ S, int n_lower, int64_t n_slabs)
+k_schur_syrk(int64_t nc, int64_t np, const double* __restrict__ Z, double* __restrict__ S, int n_lower, int64_t n_slabs,
+             const int2* __restrict__ unit_list, int64_t n_units)
 {
     extern __shared__ __align__(16) double sy_smem[];
+    __shared__ int2 ul[2][UL_CHUNK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t4 = lane & 3;
     const int wr = warp >> 2, wc = warp & 3;   // 2 x 4 warps: 48 rows x 24 columns each
 
-    const int64_t units = (int64_t)n_lower * n_slabs;
+    const int64_t units = LIST ? n_units : (int64_t)n_lower * n_slabs;
     const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
     if (u0 >= u1) return;
+    // chunk j of this CTA's range sits in ul[j & 1]; chunk j + 1 is loaded when the computation enters chunk j (the fetches
+    // run at most two units ahead of it)
+    auto load_chunk = [&](int64_t j) {
+        if (threadIdx.x < UL_CHUNK) {
+            const int64_t u = u0 + UL_CHUNK * j + threadIdx.x;
+            ul[j & 1][threadIdx.x] = u < u1 ? unit_list[u] : make_int2(-1, 0);
+        }
+    };
+    auto entry = [&](int64_t u) -> int2 { const int64_t i = u - u0; return ul[(i / UL_CHUNK) & 1][i % UL_CHUNK]; };
+    if (LIST) {
+        load_chunk(0);
+        load_chunk(1);
+        __syncthreads();
+    }
     FetchPlan<ALIGNED> fp;
     fp.init();
 
@@ -127,25 +154,35 @@ k_schur_syrk(int64_t nc, int64_t np, const double* __restrict__ Z, double* __res
             }
     };
 
-    // (tile, slab) of the unit being computed and of the unit being fetched, advanced incrementally
-    int c_tile = (int)(u0 / n_slabs), cti, ctj;
-    tile_of(c_tile, cti, ctj);
+    // (tile, slab) of the unit being computed and of the unit being fetched, advanced incrementally (or read from the list)
+    int c_tile = LIST ? 0 : (int)(u0 / n_slabs), cti = 0, ctj = 0;
+    if (!LIST) tile_of(c_tile, cti, ctj);
     int f_tile = c_tile, fti = cti, ftj = ctj;
-    int64_t f_slab = u0 % n_slabs, f_u = u0;
+    int64_t f_slab = LIST ? 0 : u0 % n_slabs, f_u = u0;
     auto fetch_next = [&](int stage) {
         if (f_u < u1) {
-            fetch_stage<ALIGNED>(fp, sy_smem + stage * STAGE_DOUBLES, Z, nc, np, fti, ftj, f_slab * SK);
-            ++f_u;
-            if (++f_slab == n_slabs) { f_slab = 0; ++f_tile; tile_of(f_tile, fti, ftj); }
+            if (LIST) {
+                const int2 e = entry(f_u);
+                fetch_stage<ALIGNED>(fp, sy_smem + stage * STAGE_DOUBLES, Z, nc, np, e.x >> 16, e.x & 0xffff, (int64_t)e.y * SK);
+                ++f_u;
+            } else {
+                fetch_stage<ALIGNED>(fp, sy_smem + stage * STAGE_DOUBLES, Z, nc, np, fti, ftj, f_slab * SK);
+                ++f_u;
+                if (++f_slab == n_slabs) { f_slab = 0; ++f_tile; tile_of(f_tile, fti, ftj); }
+            }
         }
         cp_async_commit();
     };
     for (int s = 0; s < S_STAGES - 1; ++s) fetch_next(s);
     int c_stage = 0, f_stage = S_STAGES - 1;
-    int64_t c_slab = u0 % n_slabs;
+    int64_t c_slab = LIST ? 0 : u0 % n_slabs;
     for (int64_t u = u0; u < u1; ++u) {
         cp_async_wait<S_STAGES - 2>();
         __syncthreads();   // stage u has landed for everybody; stage u - 1 has been consumed by everybody
+        if (LIST) {
+            const int64_t i = u - u0;
+            if (i > 0 && i % UL_CHUNK == 0) load_chunk(i / UL_CHUNK + 1);   // replaces the chunk everybody has left
+        }
         fetch_next(f_stage);
         f_stage = f_stage + 1 == S_STAGES ? 0 : f_stage + 1;
         const double* A = sy_smem + c_stage * STAGE_DOUBLES + wr * 48 + g;
@@ -163,20 +200,36 @@ k_schur_syrk(int64_t nc, int64_t np, const double* __restrict__ Z, double* __res
                 for (int j = 0; j < 3; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
         c_stage = c_stage + 1 == S_STAGES ? 0 : c_stage + 1;
-        if (++c_slab == n_slabs) {   // the range leaves this tile
+        if (LIST) {
+            const int2 e = entry(u);
+            if (u + 1 == u1 || entry(u + 1).x != e.x) flush(e.x >> 16, e.x & 0xffff);   // the range leaves this tile
+        } else if (++c_slab == n_slabs) {   // the range leaves this tile
             flush(cti, ctj);
             c_slab = 0;
             ++c_tile;
             tile_of(c_tile, cti, ctj);
         }
     }
-    if (c_slab != 0) flush(cti, ctj);
+    if (!LIST && c_slab != 0) flush(cti, ctj);
+}
+
+// segment s = (camera c, pose m): the row blocks (ST rows each) that camera c's 15 rows touch are non-zero for pose m
+__global__ void k_pose_block_mask(int64_t S, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose,
+                                  unsigned long long* __restrict__ mask)
+{
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int c = seg_cam[s];
+    const int b0 = 15 * c / ST, b1 = (15 * c + 14) / ST;
+    unsigned long long bits = 1ull << b0;
+    if (b1 != b0) bits |= 1ull << b1;
+    atomicOr(mask + seg_pose[s], bits);
 }
 
 }  // namespace
 
-// S (n x n, column-major, lower triangle) -= Z Z^T with Z given column-major as [k][n]
-int launch_schur_syrk(cudaStream_t st, int sm_count, int64_t n, int64_t k, const double* Z, double* S)
+// S (n x n, column-major, lower triangle) -= Z Z^T with Z given column-major as [k][n]; plan (optional): the non-zero units
+int launch_schur_syrk(cudaStream_t st, int sm_count, int64_t n, int64_t k, const double* Z, double* S, const SchurPlan* plan)
 {
     if (n <= 0 || k <= 0) return PCS_OK;
     const int n_t = (int)((n + ST - 1) / ST);
@@ -184,12 +237,79 @@ int launch_schur_syrk(cudaStream_t st, int sm_count, int64_t n, int64_t k, const
     const int64_t n_slabs = (k + SK - 1) / SK;
     const size_t smem = (size_t)S_STAGES * STAGE_DOUBLES * sizeof(double);
     const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(Z) & 15) == 0);
-    auto kern = aligned ? k_schur_syrk<true> : k_schur_syrk<false>;
+    const bool list = plan && plan->units;
+    if (list && plan->n_units == 0) return PCS_OK;
+    auto kern = list ? (aligned ? k_schur_syrk<true, true> : k_schur_syrk<false, true>) : (aligned ? k_schur_syrk<true, false> : k_schur_syrk<false, false>);
     PCS_CUDA(ensure_dynamic_smem(kern, smem));
-    const int64_t units = (int64_t)n_lower * n_slabs;
+    const int64_t units = list ? plan->n_units : (int64_t)n_lower * n_slabs;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)sm_count, units));   // two CTAs per SM
-    kern<<<grid, S_THREADS, smem, st>>>(n, k, Z, S, n_lower, n_slabs);
+    kern<<<grid, S_THREADS, smem, st>>>(n, k, Z, S, n_lower, n_slabs, list ? (const int2*)plan->units : nullptr, list ? plan->n_units : 0);
     PCS_CUDA(cudaGetLastError());
+    return PCS_OK;
+}
+
+void schur_plan_free(SchurPlan* plan)
+{
+    if (plan->pose_slot) cudaFree(plan->pose_slot);
+    if (plan->units) cudaFree(plan->units);
+    *plan = SchurPlan();
+}
+
+// Static block-sparsity plan of the pose elimination (see the header comment).  nl = logical order of the reduced system,
+// rows [15 C, nl) are the target-point rows of the self-calibration chain (treated as dense).  Leaves the plan empty (dense
+// SYRK, identity column order) when the reduced system has more than 64 row blocks or too few units would be skipped.
+int schur_plan_build(pcs_problem* p, int64_t nc, int64_t nl, SchurPlan* plan)
+{
+    schur_plan_free(plan);
+    const int n_t = (int)((nc + ST - 1) / ST);
+    const int64_t M = p->M, n_slabs = (6 * M + SK - 1) / SK;
+    if (n_t > 64 || M == 0 || p->n_seg == 0) return PCS_OK;
+    unsigned long long* d_mask = nullptr;
+    PCS_CUDA(cudaMalloc((void**)&d_mask, (size_t)M * 8));
+    std::vector<unsigned long long> mask((size_t)M);
+    cudaError_t e = cudaMemsetAsync(d_mask, 0, (size_t)M * 8, p->stream);
+    if (e == cudaSuccess) {
+        k_pose_block_mask<<<(int)((p->n_seg + 255) / 256), 256, 0, p->stream>>>(p->n_seg, p->seg_cam, p->seg_pose, d_mask);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mask.data(), d_mask, (size_t)M * 8, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(d_mask);
+    if (e != cudaSuccess) { set_error(std::string("schur_plan_build: ") + cudaGetErrorString(e)); return PCS_ERR_CUDA; }
+    const int64_t n_cam_rows = 15 * (int64_t)p->C;
+    if (nl > n_cam_rows) {   // point rows: every pose may touch them
+        unsigned long long pts = 0;
+        for (int b = (int)(n_cam_rows / ST); b <= (int)((nl - 1) / ST); ++b) pts |= 1ull << b;
+        for (auto& m : mask) if (m) m |= pts;
+    }
+    // column order: poses with the same / similar visibility pattern next to each other
+    std::vector<int32_t> order((size_t)M), slot((size_t)M);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return mask[a] < mask[b]; });
+    for (int64_t i = 0; i < M; ++i) slot[order[i]] = (int32_t)i;
+    // row blocks touched by the columns of every slab
+    std::vector<unsigned long long> slab_any((size_t)n_slabs, 0ull);
+    std::vector<int2> units;
+    const int64_t total = (int64_t)n_t * (n_t + 1) / 2 * n_slabs;
+    units.reserve((size_t)(total / 2 + 16));
+    for (int ti = 0; ti < n_t; ++ti)
+        for (int tj = 0; tj <= ti; ++tj) {
+            const unsigned long long need = (1ull << ti) | (1ull << tj);
+            for (int64_t s = 0; s < n_slabs; ++s) {
+                const int64_t p0 = SK * s / 6, p1 = std::min<int64_t>(M - 1, (SK * s + SK - 1) / 6);
+                bool nz = false;
+                for (int64_t q = p0; q <= p1 && !nz; ++q) nz = (mask[order[q]] & need) == need;
+                if (nz) units.push_back(make_int2((ti << 16) | tj, (int)s));
+            }
+        }
+    plan->fraction = total ? (double)units.size() / (double)total : 1.0;
+    if (plan->fraction > 0.85) return PCS_OK;   // nothing worth skipping: dense SYRK, identity column order
+    PCS_CUDA(cudaMalloc((void**)&plan->pose_slot, (size_t)M * 4));
+    PCS_CUDA(cudaMalloc((void**)&plan->units, std::max<size_t>(units.size(), 1) * sizeof(int2)));
+    PCS_CUDA(cudaMemcpyAsync(plan->pose_slot, slot.data(), (size_t)M * 4, cudaMemcpyHostToDevice, p->stream));
+    PCS_CUDA(cudaMemcpyAsync(plan->units, units.data(), units.size() * sizeof(int2), cudaMemcpyHostToDevice, p->stream));
+    PCS_CUDA(cudaStreamSynchronize(p->stream));   // the host vectors go out of scope
+    plan->n_units = (int64_t)units.size();
     return PCS_OK;
 }
 
@@ -208,7 +328,7 @@ extern "C" int pcs_syrk_sub(int device, int64_t n, int64_t k, const double* Z, d
     if (e == cudaSuccess) e = cudaMemcpy(dZ, Z, (size_t)(n * k) * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(dS, S, (size_t)(n * n) * 8, cudaMemcpyHostToDevice);
     int rc = PCS_OK;
-    if (e == cudaSuccess) rc = launch_schur_syrk(nullptr, sms, n, k, dZ, dS);
+    if (e == cudaSuccess) rc = launch_schur_syrk(nullptr, sms, n, k, dZ, dS, nullptr);
     if (e == cudaSuccess && rc == PCS_OK) e = cudaDeviceSynchronize();
     if (e == cudaSuccess && rc == PCS_OK) e = cudaMemcpy(S, dS, (size_t)(n * n) * 8, cudaMemcpyDeviceToHost);
     cudaFree(dZ);

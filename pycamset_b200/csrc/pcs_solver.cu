@@ -39,6 +39,7 @@ struct LmWorkspace {
     double* L = nullptr;     // [M][36] lower Cholesky factors of damped V
     double* y = nullptr;     // [M][6]  L^-1 b_p
     double* Z = nullptr;     // [np][nc] column-major (nc rows): W L^-T scattered by (camera, pose)
+    SchurPlan plan;          // static block sparsity of Z: pose column order + non-zero (tile, slab) units (pcs_schur.cu)
     double* red = nullptr;   // [S nc*nc | rhs nc | gc nc | cost 1]  (all-reduce unit)
     int64_t red_doubles = 0;
     double* delta = nullptr; // [Lparams]
@@ -152,8 +153,8 @@ constexpr int Z_CAM_WIN = 4;
 __global__ void __launch_bounds__(256)
 k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose,
                const double* __restrict__ W, const double* __restrict__ L, const double* __restrict__ y,
-               const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask, double* __restrict__ Z,
-               double* __restrict__ rhs)
+               const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask, const int32_t* __restrict__ pose_slot,
+               double* __restrict__ Z, double* __restrict__ rhs)
 {
     __shared__ double s_acc[Z_CAM_WIN * 15];
     __shared__ int s_c0;
@@ -179,7 +180,9 @@ k_lm_segment_Z(int64_t S, int64_t nc, const int32_t* __restrict__ seg_cam, const
             dot = fma(z[i], y[(int64_t)m * 6 + i], dot);
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) Z[((int64_t)m * 6 + i) * nc + (int64_t)c * 15 + a] = z[i];
+        const int64_t col0 = 6 * (int64_t)(pose_slot ? pose_slot[m] : m);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Z[(col0 + i) * nc + (int64_t)c * 15 + a] = z[i];
         const int cw = c - s_c0;
         if (dot != 0.0) {
             if (cw >= 0 && cw < Z_CAM_WIN) atomicAdd(&s_acc[cw * 15 + a], -dot);
@@ -252,7 +255,7 @@ __global__ void k_lm_init_reduced(int C, int K, int64_t nc, int64_t nl, double l
 __global__ void __launch_bounds__(256)
 k_lm_point_Z(int M, int K, int64_t nc, int64_t row0, const double* __restrict__ Ymk, const double* __restrict__ L,
              const double* __restrict__ y, const uint8_t* __restrict__ pose_mask, const uint8_t* __restrict__ key_mask,
-             double* __restrict__ Z, double* __restrict__ rhs)
+             const int32_t* __restrict__ pose_slot, double* __restrict__ Z, double* __restrict__ rhs)
 {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= (int64_t)M * K * 3) return;
@@ -278,8 +281,9 @@ k_lm_point_Z(int M, int K, int64_t nc, int64_t row0, const double* __restrict__ 
         dot = fma(z[i], y[(int64_t)m * 6 + i], dot);
     }
     const int64_t row = row0 + 3 * (int64_t)k + a;
+    const int64_t col0 = 6 * (int64_t)(pose_slot ? pose_slot[m] : m);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) Z[((int64_t)m * 6 + i) * nc + row] = z[i];
+    for (int i = 0; i < 6; ++i) Z[(col0 + i) * nc + row] = z[i];
     if (dot != 0.0) atomicAdd(rhs + row, -dot);
 }
 
@@ -295,12 +299,12 @@ __global__ void k_lm_fix_diag(int64_t nc, double* __restrict__ Smat)
 // instead of by a library GEMV over the whole of Z, then lane 0 runs the 6 x 6 back substitution.
 __global__ void __launch_bounds__(128)
 k_lm_pose_back(int M, int64_t nc, const double* __restrict__ L, const double* __restrict__ y, const double* __restrict__ Z,
-               const double* __restrict__ delta_c, double* __restrict__ delta_p)
+               const int32_t* __restrict__ pose_slot, const double* __restrict__ delta_c, double* __restrict__ delta_p)
 {
     const int m = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (m >= M) return;
     double t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const double* Zm = Z + (int64_t)m * 6 * nc;
+    const double* Zm = Z + (int64_t)(pose_slot ? pose_slot[m] : m) * 6 * nc;
     for (int64_t a = lane; a < nc; a += 32) {
         const double d = delta_c[a];
 #pragma unroll
@@ -529,6 +533,7 @@ void lm_free(pcs_problem* p)
     if (w->ne_alt && w->ne_orig && p->ne == w->ne_alt) swap_normal_buffers(p, w);
     if (w->blas) cublasDestroy(w->blas);
     if (w->solver) cusolverDnDestroy(w->solver);
+    schur_plan_free(&w->plan);
     double* ptrs[] = {w->L, w->y, w->Z, w->red, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs, w->Ldiag, w->ne_alt};
     for (double* q : ptrs) if (q) cudaFree(q);
     if (w->info) cudaFree(w->info);
@@ -596,6 +601,9 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
         PCS_CUDA(cudaMalloc((void**)&w->y, (size_t)w->np * 8));
         PCS_CUDA(cudaMalloc((void**)&w->Z, (size_t)(w->nc * w->np) * 8));
         PCS_CUDA(cudaMemsetAsync(w->Z, 0, (size_t)(w->nc * w->np) * 8, p->stream));  // sparsity pattern is static
+        // block-sparse pose elimination (PCS_LM_SCHUR=dense: full iteration space, identity column order -- A/B runs, tests)
+        const char* es = std::getenv("PCS_LM_SCHUR");
+        if (!(es && es[0] == 'd')) PCS_TRY(schur_plan_build(p, w->nc, w->nl, &w->plan));
         w->red_doubles = w->nc * w->nc + 2 * w->nc + 1;
         PCS_CUDA(cudaMalloc((void**)&w->red, (size_t)w->red_doubles * 8));
         // own persistent Cholesky solve (PCS_LM_CHOL=cusolver selects the library path for A/B runs)
@@ -648,16 +656,16 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     k_lm_pose_factor<<<grid_for(p->M, 128), 128, 0, st>>>(p->M, lambda, p->V, p->gp, p->pose_mask, w->L, w->y, w->scal);
     if (p->n_seg)
         k_lm_segment_Z<<<grid_for(p->n_seg * 15, 256), 256, 0, st>>>(p->n_seg, nc, p->seg_cam, p->seg_pose, p->W, w->L, w->y,
-                                                                     p->cam_mask, p->pose_mask, w->Z, rhs);
+                                                                     p->cam_mask, p->pose_mask, w->plan.pose_slot, w->Z, rhs);
     if (selfcal)
         k_lm_point_Z<<<grid_for((int64_t)p->M * p->K * 3, 256), 256, 0, st>>>(p->M, p->K, nc, 15 * (int64_t)p->C, p->Ymk, w->L, w->y,
-                                                                             p->pose_mask, p->key_mask, w->Z, rhs);
+                                                                             p->pose_mask, p->key_mask, w->plan.pose_slot, w->Z, rhs);
     PCS_CUDA(cudaGetLastError());
     const double minus1 = -1.0, one = 1.0;
     static const bool lib_syrk = [] { const char* e = std::getenv("PCS_LM_SYRK"); return e && e[0] == 'c'; }();   // A/B runs
     if (lib_syrk) PCS_TRY(ensure_blas(p, w));
     if (lib_syrk) PCS_BLAS(cublasDsyrk(w->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, (int)nc, (int)np, &minus1, w->Z, (int)nc, &one, Smat, (int)nc));
-    else PCS_TRY(launch_schur_syrk(st, p->sm_count, nc, np, w->Z, Smat));
+    else PCS_TRY(launch_schur_syrk(st, p->sm_count, nc, np, w->Z, Smat, &w->plan));
     if (p->allreduce) {
         int rc = p->allreduce(p->allreduce_user, w->red, w->red_doubles, 0, (void*)st);
         if (rc != 0) { set_error("all-reduce callback failed"); return PCS_ERR_CUDA; }
@@ -672,7 +680,7 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     p->n_launches += 8;
     // rhs now holds delta_c
     double* dp = w->delta + 15 * (int64_t)p->C;  // pose part of the parameter-string delta is written in place
-    k_lm_pose_back<<<grid_for((int64_t)p->M * 32, 128), 128, 0, st>>>(p->M, nc, w->L, w->y, w->Z, rhs, dp);
+    k_lm_pose_back<<<grid_for((int64_t)p->M * 32, 128), 128, 0, st>>>(p->M, nc, w->L, w->y, w->Z, w->plan.pose_slot, rhs, dp);
     const int K3 = selfcal ? 3 * p->K : 0;
     k_lm_assemble_delta<<<grid_for(15 * (int64_t)p->C + 6 * (int64_t)p->M + K3, 128), 128, 0, st>>>(
         p->C, p->M, K3, lambda, rhs, dp, p->U, p->gc, p->V, p->gp, p->Pk, p->gk, p->cam_mask, p->pose_mask, p->key_mask, p->params,
@@ -875,6 +883,16 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
         stats->lambda_final = lambda; stats->seconds = ms * 1e-3;
     }
     return rc;
+}
+
+int pcs_lm_schur_fraction(pcs_problem* p, double* fraction)
+{
+    PCS_REQUIRE(p && fraction, "NULL argument");
+    PCS_CUDA(cudaSetDevice(p->device));
+    PCS_TRY(lm_prepare(p));
+    const LmWorkspace* w = (const LmWorkspace*)p->lm_ws;
+    *fraction = w->plan.units ? w->plan.fraction : 1.0;
+    return PCS_OK;
 }
 
 int pcs_lm_solve(pcs_problem* p, const double* x0, const pcs_lm_options* opts_in, double* x_out, pcs_lm_stats* stats)

@@ -225,6 +225,12 @@ class BundleProblem:
         L.check(self._lib.pcs_device_buffers_get(self._h, ct.byref(b)))
         return b
 
+    def lm_schur_fraction(self) -> float:
+        """Fraction of the (tile pair, slab) units the block-sparse pose elimination of lm_solve visits (1.0 = dense)."""
+        f = ct.c_double()
+        L.check(self._lib.pcs_lm_schur_fraction(self._h, ct.byref(f)))
+        return f.value
+
     def timing_enable(self, on=True):
         L.check(self._lib.pcs_timing_enable(self._h, 1 if on else 0))
 

@@ -27,3 +27,41 @@ def test_syrk_matches_numpy(n, k):
     assert np.all(np.abs(S[lo] - ref[lo]) <= bound[lo])
     up = np.triu_indices(n, 1)
     assert np.array_equal(S[up], S0[up])   # the strict upper triangle is not touched
+
+
+def _ring_lm(max_iter, dense):
+    """LM iterates of a 32-camera ring (every pose seen by about half of the cameras) with / without the sparsity plan."""
+    import os
+    from pycamset_b200 import synthetic as syn
+    from pycamset_b200.problem import BundleProblem
+    rig = syn.make_rig(32, 120, distortion=True, seed=3, detect_prob=0.9)
+    intr, extr, poses = rig.perturbed(np.random.default_rng(5), 2e-3)
+    params = rig.param_string(intr, extr, poses)
+    unfixed = np.ones(params.shape[0], bool)
+    unfixed[15 * 32:15 * 32 + 6] = False
+    old = os.environ.pop("PCS_LM_SCHUR", None)
+    if dense:
+        os.environ["PCS_LM_SCHUR"] = "dense"   # read when the solver workspace is built
+    try:
+        with BundleProblem(0, rig.cam.numpy(), rig.pose.numpy(), rig.key.numpy(), rig.uv.numpy(), 32, 120, 81, template=rig.template,
+                           unfixed=unfixed) as p:
+            p.set_param_string(params)
+            frac = p.lm_schur_fraction()
+            x, st = p.lm_solve(params[unfixed], max_iter=max_iter, ftol=0, xtol=0, gtol=0)
+    finally:
+        os.environ.pop("PCS_LM_SCHUR", None)
+        if old is not None:
+            os.environ["PCS_LM_SCHUR"] = old
+    return frac, x, st
+
+
+def test_block_sparse_pose_elimination_equals_the_dense_one():
+    """The unit list skips only (tile pair, slab) units whose product is exactly zero and the permuted pose columns are
+    summed in a different order: same LM iterates up to FP64 summation order."""
+    f_sparse, x_s, st_s = _ring_lm(6, dense=False)
+    f_dense, x_d, st_d = _ring_lm(6, dense=True)
+    assert f_dense == 1.0
+    assert 0.2 < f_sparse < 0.85, f_sparse          # the plan is active and skips a substantial part of the units
+    assert st_s["iterations"] == st_d["iterations"]
+    assert abs(st_s["cost_final"] - st_d["cost_final"]) <= 1e-9 * st_d["cost_final"]
+    assert np.max(np.abs(x_s - x_d)) <= 1e-7 * max(1.0, np.max(np.abs(x_d)))
