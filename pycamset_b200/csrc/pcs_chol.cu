@@ -306,7 +306,12 @@ k_chol_solve(CholProblem P)
     double* T = Pk + TILE_DOUBLES;             // the tile being processed
     double* X = T + TILE_DOUBLES;              // L_{i,k-1}
     double* Y = X + TILE_DOUBLES;              // L_{j,k-1}
-    double* invd = Y + TILE_DOUBLES;           // [32]
+    double* T2 = Y + TILE_DOUBLES;             // 2 x 2 groups of trailing tiles: three more tiles, a second row / column operand
+    double* T3 = T2 + TILE_DOUBLES;
+    double* T4 = T3 + TILE_DOUBLES;
+    double* X2 = T4 + TILE_DOUBLES;
+    double* Y2 = X2 + TILE_DOUBLES;
+    double* invd = Y2 + TILE_DOUBLES;          // [32]
     double* colbuf = invd + TB;                // [2][32]
     double* yv = colbuf + 2 * TB;              // [nb * 32] back substitution (CTA 0)
     double* RB = yv + P.nb * TB;               // [(nb - 1) * 32][RB_STRIDE] row block of L (CTA 0)
@@ -359,22 +364,72 @@ k_chol_solve(CholProblem P)
             trace_stamp(P, k, 2);
             trace_stamp(P, k, 6);
         }
-        for (int t = t_next; t < n_tiles; t += gridDim.x) {
-            int bi, bj;
-            phase_tile(k, nb, t, bi, bj);
-            const bool panel = bj == k;   // only when the grid is narrower than the panel
-            tile_fetch(P, bi, bj, T);
-            if (k > 0) { tile_fetch(P, bi, k - 1, X); if (!panel) tile_fetch(P, bj, k - 1, Y); }
-            cp_async_wait_all();
-            __syncthreads();
-            if (k > 0) tile_update<0, CH_WARPS>(T, X, panel ? Pk : Y);
-            __syncthreads();
-            if (panel) {
-                if (warp == 0) tile_trsm(T, D, invd, lane);
+        if (n_panel <= (int)gridDim.x) {
+            // Trailing tiles (lagged update with panel k - 1) in 2 x 2 groups: rows I, I + 1 x columns J, J + 1 of the lower
+            // triangle share their operands L_{I,k-1}, L_{I+1,k-1}, L_{J,k-1}, L_{J+1,k-1}, and all (up to) eight tiles of
+            // a group are in flight together -- a visit is bound by the latency of its fetches from L2, not by the updates
+            // (2.9 us per single-tile visit with three fetches; a group does four updates on eight fetches in one round
+            // trip).  Groups are dealt round-robin, starting with the CTAs that have no panel tile in this phase.
+            if (k > 0) {
+                const int n_pairs = (nb - k + 1) / 2;                  // row pairs of rows k + 1 .. nb (the last one may be single)
+                const int n_groups = n_pairs * (n_pairs + 1) / 2;
+                int g0 = ((int)blockIdx.x - n_panel) % (int)gridDim.x;
+                if (g0 < 0) g0 += gridDim.x;
+                for (int g = g0; g < n_groups; g += gridDim.x) {
+                    int a = 0, rem = g;
+                    while (rem > a) { rem -= a + 1; ++a; }             // group (a, b), b <= a, row-major over the lower triangle
+                    const int b = rem;
+                    const int I = k + 1 + 2 * a, J = k + 1 + 2 * b;
+                    const bool diag = a == b;
+                    const bool r1 = I + 1 <= nb;                       // second row of the pair exists
+                    // members: (I, J), (I + 1, J), (I + 1, J + 1) and, off the diagonal, (I, J + 1); columns stop at nb - 1
+                    const bool m00 = J <= nb - 1, m10 = r1 && J <= nb - 1, m11 = r1 && J + 1 <= nb - 1 && J + 1 <= I + 1,
+                               m01 = !diag && J + 1 <= nb - 1;
+                    double* const Yj = diag ? X : Y;                   // on the diagonal the column operands are the row operands
+                    double* const Yj1 = diag ? X2 : Y2;
+                    if (m00) tile_fetch(P, I, J, T);
+                    if (m10) tile_fetch(P, I + 1, J, T2);
+                    if (m11) tile_fetch(P, I + 1, J + 1, T3);
+                    if (m01) tile_fetch(P, I, J + 1, T4);
+                    tile_fetch(P, I, k - 1, X);
+                    if (r1) tile_fetch(P, I + 1, k - 1, X2);
+                    if (!diag) {
+                        tile_fetch(P, J, k - 1, Y);
+                        if (m01 || m11) tile_fetch(P, J + 1, k - 1, Y2);
+                    }
+                    cp_async_wait_all();
+                    __syncthreads();
+                    if (m00) tile_update<0, CH_WARPS>(T, X, Yj);
+                    if (m10) tile_update<0, CH_WARPS>(T2, X2, Yj);
+                    if (m11) tile_update<0, CH_WARPS>(T3, X2, Yj1);
+                    if (m01) tile_update<0, CH_WARPS>(T4, X, Yj1);
+                    __syncthreads();
+                    if (m00) tile_store(P, I, J, T);
+                    if (m10) tile_store(P, I + 1, J, T2);
+                    if (m11) tile_store(P, I + 1, J + 1, T3);
+                    if (m01) tile_store(P, I, J + 1, T4);
+                    __syncthreads();
+                }
+            }
+        } else {
+            // the grid is narrower than the panel (n > 32 x grid): one tile per visit, panel tiles included
+            for (int t = t_next; t < n_tiles; t += gridDim.x) {
+                int bi, bj;
+                phase_tile(k, nb, t, bi, bj);
+                const bool panel = bj == k;
+                tile_fetch(P, bi, bj, T);
+                if (k > 0) { tile_fetch(P, bi, k - 1, X); if (!panel) tile_fetch(P, bj, k - 1, Y); }
+                cp_async_wait_all();
+                __syncthreads();
+                if (k > 0) tile_update<0, CH_WARPS>(T, X, panel ? Pk : Y);
+                __syncthreads();
+                if (panel) {
+                    if (warp == 0) tile_trsm(T, D, invd, lane);
+                    __syncthreads();
+                }
+                tile_store(P, bi, bj, T);
                 __syncthreads();
             }
-            tile_store(P, bi, bj, T);
-            __syncthreads();
         }
         trace_stamp(P, k, 3);
         grid_barrier(P.bar, P.bar_base + (unsigned long long)(k + 1) * gridDim.x, P.info);
@@ -491,14 +546,14 @@ k_chol_solve(CholProblem P)
 
 size_t chol_smem_bytes(int nb, int rb_cols)
 {
-    return (size_t)(5 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)rb_cols * RB_STRIDE) * sizeof(double);
+    return (size_t)(10 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)rb_cols * RB_STRIDE) * sizeof(double);
 }
 
 // capacity of the row-block buffer: the whole longest row block when it fits the opt-in shared memory, else what fits
 int chol_rb_cols(int nb, int max_optin_bytes)
 {
     const int want = std::max(nb - 1, 0) * TB;
-    const long long fixed = (long long)(5 * TILE_DOUBLES + 3 * TB + nb * TB) * (long long)sizeof(double) + 1024;
+    const long long fixed = (long long)(10 * TILE_DOUBLES + 3 * TB + nb * TB) * (long long)sizeof(double) + 1024;
     const long long room = ((long long)max_optin_bytes - fixed) / (long long)(RB_STRIDE * sizeof(double));
     const int cap = (int)std::max<long long>(0, room / TB * TB);
     return std::min(want, cap);

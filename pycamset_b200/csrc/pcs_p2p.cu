@@ -14,6 +14,8 @@ namespace pcs {
 
 constexpr int P2P_MAX_WORLD = 16;
 constexpr int64_t P2P_FLAG_DOUBLES = 32;   // 16 x uint64 flags, padded to 256 bytes
+constexpr int P2P_ILP = 8;                 // push: entries per thread and pass with their loads in flight together
+constexpr int P2P_SUM_ILP = 4;             // sum: entries per thread and pass (x world loads each)
 
 struct P2PPeers {
     double* buf[P2P_MAX_WORLD];
@@ -54,11 +56,24 @@ k_p2p_allreduce(double* __restrict__ local, int64_t n, int rank, int world_rt, P
     const int tid = threadIdx.x;
     const int64_t data = P2P_FLAG_DOUBLES + (int64_t)(epoch & 1) * world * n;
     pdl_wait();   // launched behind the normal-equation kernel with programmatic serialisation: its sums are complete from here on
-    for (int64_t i = tid; i < n; i += blockDim.x) {
-        const double v = local[i];
+    // P2P_ILP entries per thread and pass: all loads of a pass are in flight together (the exchange is a chain of memory
+    // round trips; one entry per trip made it 8 dependent L2 / NVLink latencies long)
+    for (int64_t i0 = 0; i0 < n; i0 += (int64_t)P2P_ILP * blockDim.x) {
+        double v[P2P_ILP];
 #pragma unroll
-        for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
-            if (r < world) peers.buf[r][data + (int64_t)rank * n + i] = v;
+        for (int u = 0; u < P2P_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            v[u] = i < n ? local[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < P2P_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            if (i < n) {
+#pragma unroll
+                for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+                    if (r < world) peers.buf[r][data + (int64_t)rank * n + i] = v[u];
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -69,12 +84,23 @@ k_p2p_allreduce(double* __restrict__ local, int64_t n, int rank, int world_rt, P
         while (ld_acquire_sys(theirs) < epoch) { }
     }
     __syncthreads();
-    for (int64_t i = tid; i < n; i += blockDim.x) {
-        double s = 0.0;
+    for (int64_t i0 = 0; i0 < n; i0 += (int64_t)P2P_SUM_ILP * blockDim.x) {
+        double s[P2P_SUM_ILP];
 #pragma unroll
-        for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
-            if (r < world) s += ld_relaxed_sys(mine + data + (int64_t)r * n + i);   // rank order: identical bits everywhere
-        local[i] = s;
+        for (int u = 0; u < P2P_SUM_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            s[u] = 0.0;
+            if (i < n) {
+#pragma unroll
+                for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+                    if (r < world) s[u] += ld_relaxed_sys(mine + data + (int64_t)r * n + i);   // rank order: identical bits everywhere
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < P2P_SUM_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            if (i < n) local[i] = s[u];
+        }
     }
 }
 
@@ -94,8 +120,19 @@ k_p2p_allreduce_multi(double* __restrict__ local, int64_t n, int rank, int world
         double* dst = peers.buf[b] + data + (int64_t)rank * n;
         const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(local)) & 15) == 0;
         const int64_t n2 = vec ? n / 2 : 0;
-        for (int64_t i = tid; i < n2; i += blockDim.x)
-            reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(local)[i];
+        for (int64_t i0 = 0; i0 < n2; i0 += (int64_t)P2P_ILP * blockDim.x) {   // loads of a pass in flight together
+            double2 v[P2P_ILP];
+#pragma unroll
+            for (int u = 0; u < P2P_ILP; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+                if (i < n2) v[u] = reinterpret_cast<const double2*>(local)[i];
+            }
+#pragma unroll
+            for (int u = 0; u < P2P_ILP; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+                if (i < n2) reinterpret_cast<double2*>(dst)[i] = v[u];
+            }
+        }
         for (int64_t i = 2 * n2 + tid; i < n; i += blockDim.x) dst[i] = local[i];
     }
     __threadfence_system();
@@ -113,13 +150,24 @@ k_p2p_allreduce_multi(double* __restrict__ local, int64_t n, int rank, int world
         while (ld_acquire_sys(done) < epoch * (uint64_t)world) { }
     }
     __syncthreads();
-    const int64_t i0 = n * b / world, i1 = n * (b + 1) / world;
-    for (int64_t i = i0 + tid; i < i1; i += blockDim.x) {
-        double s = 0.0;
+    const int64_t e0 = n * b / world, e1 = n * (b + 1) / world;
+    for (int64_t i0 = e0; i0 < e1; i0 += (int64_t)P2P_SUM_ILP * blockDim.x) {
+        double s[P2P_SUM_ILP];
 #pragma unroll
-        for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
-            if (r < world) s += ld_relaxed_sys(mine + data + (int64_t)r * n + i);   // rank order: identical bits everywhere
-        local[i] = s;
+        for (int u = 0; u < P2P_SUM_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            s[u] = 0.0;
+            if (i < e1) {
+#pragma unroll
+                for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+                    if (r < world) s[u] += ld_relaxed_sys(mine + data + (int64_t)r * n + i);   // rank order: identical bits everywhere
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < P2P_SUM_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            if (i < e1) local[i] = s[u];
+        }
     }
 }
 

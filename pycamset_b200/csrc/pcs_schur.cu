@@ -263,7 +263,8 @@ int schur_plan_build(pcs_problem* p, int64_t nc, int64_t nl, SchurPlan* plan)
     schur_plan_free(plan);
     const int n_t = (int)((nc + ST - 1) / ST);
     const int64_t M = p->M, n_slabs = (6 * M + SK - 1) / SK;
-    if (n_t > 64 || M == 0 || p->n_seg == 0) return PCS_OK;
+    // small systems: the whole update takes microseconds, the plan (allocations, a read-back, host-side sorting) milliseconds
+    if (n_t > 64 || n_t < 3 || M < 256 || p->n_seg == 0) return PCS_OK;
     unsigned long long* d_mask = nullptr;
     PCS_CUDA(cudaMalloc((void**)&d_mask, (size_t)M * 8));
     std::vector<unsigned long long> mask((size_t)M);

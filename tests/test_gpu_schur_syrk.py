@@ -34,7 +34,7 @@ def _ring_lm(max_iter, dense):
     import os
     from pycamset_b200 import synthetic as syn
     from pycamset_b200.problem import BundleProblem
-    rig = syn.make_rig(32, 120, distortion=True, seed=3, detect_prob=0.9)
+    rig = syn.make_rig(32, 300, distortion=True, seed=3, detect_prob=0.9)
     intr, extr, poses = rig.perturbed(np.random.default_rng(5), 2e-3)
     params = rig.param_string(intr, extr, poses)
     unfixed = np.ones(params.shape[0], bool)
@@ -43,7 +43,7 @@ def _ring_lm(max_iter, dense):
     if dense:
         os.environ["PCS_LM_SCHUR"] = "dense"   # read when the solver workspace is built
     try:
-        with BundleProblem(0, rig.cam.numpy(), rig.pose.numpy(), rig.key.numpy(), rig.uv.numpy(), 32, 120, 81, template=rig.template,
+        with BundleProblem(0, rig.cam.numpy(), rig.pose.numpy(), rig.key.numpy(), rig.uv.numpy(), 32, 300, 81, template=rig.template,
                            unfixed=unfixed) as p:
             p.set_param_string(params)
             frac = p.lm_schur_fraction()

@@ -16,4 +16,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k $K -c 600 --csv --l
 ncu --set full --clock-control none --import-source on -k 'regex:^k_normal$' -c 1 -s 3 -o $O/prof_r2_kne_fp64 -f python bench.py --steps 3 --warmup 3 --no-cpu --no-lm --no-config5 --no-lm-e2e > $O/ncu_kne.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_normal_mixed -c 1 -s 3 -o $O/prof_r2_kne_mixed -f python bench.py --steps 3 --warmup 3 --no-cpu --no-lm --no-config5 --no-lm-e2e > $O/ncu_kne_mixed.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_residual -c 1 -s 3 -o $O/prof_r2_kres -f python bench.py --steps 3 --warmup 3 --no-cpu --no-lm --no-config5 --no-lm-e2e > $O/ncu_kres.log 2>&1
-ls -la $O/*.ncu-rep | tail -4
+ncu --set full --clock-control none --import-source on -k regex:k_jacobian -c 1 -s 3 -o $O/prof_r2_kjac -f python bench.py --steps 3 --warmup 3 --no-cpu --no-lm --no-config5 --no-lm-e2e > $O/ncu_kjac.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_schur_syrk -c 1 -s 2 -o $O/prof_r2_syrk -f python tools/lm_profile.py 4 ring32 > $O/ncu_syrk.log 2>&1
+ls -la $O/*.ncu-rep | tail -6
