@@ -30,6 +30,7 @@ constexpr int TILE_DOUBLES = TB * TP;
 constexpr int CHOL_THREADS = 128;
 constexpr int CH_WARPS = CHOL_THREADS / 32;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned long long XSENTINEL = 0x7ff8deadbeefcafeull;   // a NaN payload no computation produces: "x not published yet"
 
 struct CholProblem {
     double* A;        // [n][ld] column-major, lower triangle
@@ -40,7 +41,7 @@ struct CholProblem {
     int* info;
     int64_t n, ld;
     int nb;
-    int rb_cols;        // capacity (columns, multiple of 32) of the row-block buffer of the back substitution
+    double* xbuf;                // [nb * 32] back substitution mailbox: x as it is published (XSENTINEL = not yet)
     long long* trace;   // optional [nb + 1][8] globaltimer stamps of CTA 0 (tools/chol_trace.cu), else nullptr
 };
 
@@ -59,6 +60,9 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Shared-memory tiles are COLUMN-major, S[c * TP + r] = element (r, c): that is the layout of the matrix in global
 // memory, so a full tile moves with 16-byte asynchronous copies (two rows of one column per copy) and a factored
@@ -295,7 +299,6 @@ __device__ __forceinline__ void phase_tile(int k, int nb, int t, int& bi, int& b
     bi = -1; bj = -1;
 }
 
-constexpr int RB_STRIDE = TB + 2;   // row-block buffer of the back substitution: column c at RB + c * RB_STRIDE
 
 __global__ void __launch_bounds__(CHOL_THREADS)
 k_chol_solve(CholProblem P)
@@ -313,12 +316,14 @@ k_chol_solve(CholProblem P)
     double* Y2 = X2 + TILE_DOUBLES;
     double* invd = Y2 + TILE_DOUBLES;          // [32]
     double* colbuf = invd + TB;                // [2][32]
-    double* yv = colbuf + 2 * TB;              // [nb * 32] back substitution (CTA 0)
-    double* RB = yv + P.nb * TB;               // [(nb - 1) * 32][RB_STRIDE] row block of L (CTA 0)
+    double* yk = colbuf + 2 * TB;              // [32] back substitution: right-hand side of the block being solved
     __shared__ int s_bad;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb = P.nb;
     if (threadIdx.x == 0) s_bad = 0;
+    // the mailbox of the back substitution is emptied here; the grid barriers of the factorisation publish that
+    for (int e = blockIdx.x * CHOL_THREADS + threadIdx.x; e < nb * TB; e += gridDim.x * CHOL_THREADS)
+        reinterpret_cast<unsigned long long*>(P.xbuf)[e] = XSENTINEL;
 
     for (int k = 0; k < nb; ++k) {
         const int n_panel = nb - k;
@@ -435,128 +440,107 @@ k_chol_solve(CholProblem P)
         grid_barrier(P.bar, P.bar_base + (unsigned long long)(k + 1) * gridDim.x, P.info);
         trace_stamp(P, k, 4);
     }
-    if (blockIdx.x != 0) return;
-    if (threadIdx.x == 0 && s_bad) *P.info = 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && s_bad) *P.info = 1;
 
-    // Back substitution x = L^-T y by CTA 0.  Step k: warp 0 solves L_kk^T x_k = y_k (Ldiag block k, row-major, fetched
-    // one step ahead) while row block k of L (32 x 32 k) streams into shared memory; then every thread owns columns of
-    // that block and subtracts its share from y.
+    // Back substitution x = L^-T y, distributed over the grid as a dataflow (no grid barrier): block column k belongs to
+    // CTA (nb - 1 - k) mod grid.  Its owner starts from y_k, subtracts L_ik^T x_i for i = nb - 1 .. k + 1 as the x_i are
+    // published (tiles of the block column stream through a ring of shared-memory buffers ahead of the flags), solves the
+    // 32 x 32 triangle L_kk^T x_k = y_k in one warp and publishes x_k: besides the result in `rhs` it is written into a
+    // mailbox that was filled with a sentinel NaN at kernel start -- the consumers poll the values they need themselves, so
+    // the arrival of the data IS the signal (no fence + flag + second load on the chain; 8-byte stores are atomic).
+    // Every CTA walks its blocks in descending order and a block only waits for higher blocks, so the
+    // highest unfinished block can always proceed (all CTAs are co-resident: cooperative launch).  The critical path is one
+    // flag round trip + one tile product + one triangle per block; a single CTA streaming all of L (round 1) took 225 us at
+    // n = 1504 and 350 us at n = 1920.
     trace_stamp(P, nb, 0);
-    for (int e = threadIdx.x; e < nb * TB; e += CHOL_THREADS) yv[e] = e < P.n ? __ldcg(P.rhs + e) : 0.0;
-    for (int e = threadIdx.x; e < TB * (TB / 2); e += CHOL_THREADS) {
-        const int r = e >> 4, c = (e & 15) * 2;
-        cp_async16(D + r * TP + c, P.Ldiag + (int64_t)(nb - 1) * TB * TB + r * TB + c);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    for (int k = nb - 1; k >= 0; --k) {
-        double* cur = ((nb - 1 - k) & 1) ? Pk : D;
-        double* nxt = ((nb - 1 - k) & 1) ? D : Pk;
-        const int rows = (int)::min((long long)TB, (long long)(P.n - (int64_t)TB * k));
-        const int ncol = k * TB;
-        // Row block k of L goes through shared memory, RB[c][r] = L[32 k + r][c0 + c], in chunks of at most rb_cols
-        // columns: asynchronous 16-byte copies when the addresses allow it (even leading dimension, full block), guarded
-        // loads otherwise.  The first chunk and the next diagonal block are in flight while warp 0 solves the triangle.
-        const bool fast = (P.ld % 2 == 0) && rows == TB;
-        auto fetch_chunk = [&](int c0, int nc, int first_thread) {
-            const int nthr = CHOL_THREADS - first_thread;
-            if (fast) {
-                for (int e = threadIdx.x - first_thread; e < nc * (TB / 2); e += nthr) {
-                    if (e < 0) break;
-                    const int c = e >> 4, r = (e & 15) * 2;
-                    cp_async16(RB + c * RB_STRIDE + r, P.A + (int64_t)(c0 + c) * P.ld + (int64_t)TB * k + r);
-                }
-            } else {
-                for (int e0 = threadIdx.x - first_thread; e0 < nc * TB; e0 += 8 * nthr) {
-                    if (e0 < 0) break;
-                    double v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int e = e0 + u * nthr;
-                        const int c = e >> 5, r = e & 31;
-                        v[u] = (e < nc * TB && r < rows) ? __ldcg(P.A + (int64_t)(c0 + c) * P.ld + (int64_t)TB * k + r) : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int e = e0 + u * nthr;
-                        if (e < nc * TB) RB[(e >> 5) * RB_STRIDE + (e & 31)] = v[u];
-                    }
-                }
-            }
-        };
-        const int nc0 = ::min(ncol, P.rb_cols);
-        if (fast) fetch_chunk(0, nc0, 0);
-        if (k > 0)
+    {
+        double* const ring[8] = {T, X, Y, T2, T3, T4, X2, Y2};
+        constexpr int RING = 8;
+        const int c = threadIdx.x >> 2, q = threadIdx.x & 3;      // thread (c, q): column c of a tile, rows 8 q .. 8 q + 7
+        for (int k = nb - 1 - (int)blockIdx.x; k >= 0; k -= gridDim.x) {
+            // diagonal block (row-major lower factor) and y_k
             for (int e = threadIdx.x; e < TB * (TB / 2); e += CHOL_THREADS) {
-                const int r = e >> 4, c = (e & 15) * 2;
-                cp_async16(nxt + r * TP + c, P.Ldiag + (int64_t)(k - 1) * TB * TB + r * TB + c);
+                const int r = e >> 4, cc = (e & 15) * 2;
+                cp_async16(D + r * TP + cc, P.Ldiag + (int64_t)k * TB * TB + r * TB + cc);
             }
-        if (warp == 0) {
-            double yc = yv[k * TB + lane];
-            double lcol[TB];                    // column `lane` of L_kk: lcol[r] = L[r][lane]
-#pragma unroll
-            for (int r = 0; r < TB; ++r) lcol[r] = cur[r * TP + lane];
-            __syncwarp();                       // scheduling fence (see tile_factor)
-            const double inv = rcp_newton(cur[lane * TP + lane]);
-#pragma unroll
-            for (int r = TB - 1; r >= 0; --r) {
-                const double xr = __shfl_sync(FULL, yc * inv, r);
-                if (lane == r) yc = xr;
-                else if (lane < r) yc = fma(-lcol[r], xr, yc);
+            cp_async_commit();
+            const int n_up = nb - 1 - k;                          // tiles (i, k), i = nb - 1 .. k + 1
+            int issued = 0;
+            for (int gq = 0; gq < RING - 1; ++gq) {               // always RING - 1 groups (empty ones past the last tile): tile u is group u + 1
+                if (issued < n_up) { tile_fetch(P, nb - 1 - issued, k, ring[issued % RING]); ++issued; }
+                cp_async_commit();
             }
-            yv[k * TB + lane] = yc;
-        } else if (!fast) {
-            fetch_chunk(0, nc0, 32);
-        }
-        cp_async_wait_all();
-        __syncthreads();
-        double xk[TB];
-#pragma unroll
-        for (int r = 0; r < TB; r += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(yv + k * TB + r);
-            xk[r] = v.x; xk[r + 1] = v.y;
-        }
-        for (int c0 = 0; c0 < ncol; c0 += P.rb_cols) {
-            const int nc = ::min(ncol - c0, P.rb_cols);
-            if (c0 > 0) {                        // later chunks of a long row block: fetched by all threads
-                fetch_chunk(c0, nc, 0);
-                cp_async_wait_all();
+            double acc = 0.0;                                     // threads with q == 0: (sum_i L_ik^T x_i)[c]
+            for (int u = 0; u < n_up; ++u) {
+                const int i = nb - 1 - u;
+                if (issued < n_up) { tile_fetch(P, nb - 1 - issued, k, ring[issued % RING]); ++issued; }
+                cp_async_commit();                                // (possibly empty: keeps the group count uniform)
+                cp_async_wait_group<RING - 1>();                  // tile u (and the diagonal block) have landed
                 __syncthreads();
-            }
-            for (int c = threadIdx.x; c < nc; c += CHOL_THREADS) {
-                const double* col = RB + c * RB_STRIDE;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                // x_i: every thread polls the eight values it needs until none of them is the sentinel
+                const double* S = ring[u % RING] + c * TP + 8 * q;
+                const unsigned long long* xb = reinterpret_cast<const unsigned long long*>(P.xbuf) + (int64_t)TB * i + 8 * q;
+                unsigned long long xv[8];
+                int spins = 0;
+                bool ready;
+                do {
+                    ready = true;
 #pragma unroll
-                for (int r = 0; r < TB; r += 4) {
-                    const double2 l0 = *reinterpret_cast<const double2*>(col + r);
-                    const double2 l1 = *reinterpret_cast<const double2*>(col + r + 2);
-                    s0 = fma(l0.x, xk[r], s0);
-                    s1 = fma(l0.y, xk[r + 1], s1);
-                    s2 = fma(l1.x, xk[r + 2], s2);
-                    s3 = fma(l1.y, xk[r + 3], s3);
+                    for (int r = 0; r < 8; ++r) {
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(xv[r]) : "l"(xb + r) : "memory");
+                        ready = ready && xv[r] != XSENTINEL;
+                    }
+                } while (!ready && ++spins < (1 << 22));
+                if (!ready) {                                     // a block was never published: give up instead of hanging
+                    *P.info = -2;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) xv[r] = 0ull;
                 }
-                yv[c0 + c] -= (s0 + s1) + (s2 + s3);
+                double part = 0.0;
+#pragma unroll
+                for (int r = 0; r < 8; r += 2) {
+                    const double2 l = *reinterpret_cast<const double2*>(S + r);
+                    part = fma(l.x, __longlong_as_double((long long)xv[r]), part);
+                    part = fma(l.y, __longlong_as_double((long long)xv[r + 1]), part);
+                }
+                part += __shfl_xor_sync(FULL, part, 1);
+                part += __shfl_xor_sync(FULL, part, 2);
+                acc += part;
+                __syncthreads();                                  // the buffer of tile u may be refilled
+            }
+            cp_async_wait_all();
+            if (q == 0) {
+                const int64_t gi = (int64_t)TB * k + c;
+                yk[c] = (gi < P.n ? __ldcg(P.rhs + gi) : 0.0) - acc;
             }
             __syncthreads();
+            if (warp == 0) {
+                double yc = yk[lane];
+                double lcol[TB];                    // column `lane` of L_kk: lcol[r] = L[r][lane]
+#pragma unroll
+                for (int r = 0; r < TB; ++r) lcol[r] = D[r * TP + lane];
+                __syncwarp();                       // scheduling fence (see tile_factor)
+                const double inv = rcp_newton(D[lane * TP + lane]);
+#pragma unroll
+                for (int r = TB - 1; r >= 0; --r) {
+                    const double xr = __shfl_sync(FULL, yc * inv, r);
+                    if (lane == r) yc = xr;
+                    else if (lane < r) yc = fma(-lcol[r], xr, yc);
+                }
+                const int64_t gi = (int64_t)TB * k + lane;
+                const double xo = gi < P.n ? yc : 0.0;            // padding rows publish a zero: nobody waits for them forever
+                asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(P.xbuf + (int64_t)TB * k + lane), "d"(xo) : "memory");
+                if (gi < P.n) P.rhs[gi] = yc;
+            }
+            __syncthreads();                        // D / yk are reused by the next block of this CTA
         }
     }
-    for (int e = threadIdx.x; e < P.n; e += CHOL_THREADS) P.rhs[e] = yv[e];
     trace_stamp(P, nb, 1);
 }
 
-size_t chol_smem_bytes(int nb, int rb_cols)
+size_t chol_smem_bytes()
 {
-    return (size_t)(10 * TILE_DOUBLES + 3 * TB + nb * TB + (size_t)rb_cols * RB_STRIDE) * sizeof(double);
-}
-
-// capacity of the row-block buffer: the whole longest row block when it fits the opt-in shared memory, else what fits
-int chol_rb_cols(int nb, int max_optin_bytes)
-{
-    const int want = std::max(nb - 1, 0) * TB;
-    const long long fixed = (long long)(10 * TILE_DOUBLES + 3 * TB + nb * TB) * (long long)sizeof(double) + 1024;
-    const long long room = ((long long)max_optin_bytes - fixed) / (long long)(RB_STRIDE * sizeof(double));
-    const int cap = (int)std::max<long long>(0, room / TB * TB);
-    return std::min(want, cap);
+    return (size_t)(10 * TILE_DOUBLES + 4 * TB) * sizeof(double);
 }
 
 }  // namespace
@@ -570,16 +554,16 @@ int chol_prepare(int device, int64_t n, double** Ldiag, unsigned long long** bar
     PCS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     PCS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     PCS_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    const int rb_cols = chol_rb_cols(nb, max_optin);
-    const size_t smem = chol_smem_bytes(nb, rb_cols);
-    if (!coop || smem > (size_t)max_optin || (nb > 1 && rb_cols < TB)) return PCS_OK;
+    const size_t smem = chol_smem_bytes();
+    if (!coop || smem > (size_t)max_optin) return PCS_OK;
     // monotone per (kernel, device): a later, smaller problem must not lower the opt-in of a live larger one
     PCS_CUDA(ensure_dynamic_smem(k_chol_solve, smem));
     int per_sm = 0;
     PCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_solve, CHOL_THREADS, smem));
     if (per_sm < 1) return PCS_OK;
     const int n_tiles0 = nb + nb * (nb + 1) / 2;   // upper bound of the tiles of a phase
-    PCS_CUDA(cudaMalloc((void**)Ldiag, (size_t)nb * TB * TB * sizeof(double)));
+    // diagonal-block factors, followed by the mailbox of the back substitution (nb x 32 doubles, reset by every launch)
+    PCS_CUDA(cudaMalloc((void**)Ldiag, ((size_t)nb * TB * TB + (size_t)nb * TB) * sizeof(double)));
     PCS_CUDA(cudaMalloc((void**)bar, sizeof(unsigned long long)));
     PCS_CUDA(cudaMemset(*bar, 0, sizeof(unsigned long long)));
     *grid = std::max(1, std::min(sms, n_tiles0));
@@ -595,14 +579,11 @@ int launch_chol_solve(cudaStream_t st, int grid, int64_t n, double* A, int64_t l
     P.trace = trace;
     P.A = A; P.rhs = rhs; P.Ldiag = Ldiag; P.bar = bar; P.info = info; P.n = n; P.ld = ld;
     P.nb = (int)((n + TB - 1) / TB);
-    int dev = 0, max_optin = 0;
-    PCS_CUDA(cudaGetDevice(&dev));
-    PCS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    P.rb_cols = std::max(chol_rb_cols(P.nb, max_optin), TB);
+    P.xbuf = Ldiag + (size_t)P.nb * TB * TB;
     P.bar_base = *bar_base;
     *bar_base += (unsigned long long)P.nb * (unsigned long long)grid;
     void* args[] = {&P};
-    PCS_CUDA(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_THREADS), args, chol_smem_bytes(P.nb, chol_rb_cols(P.nb, max_optin)), st));
+    PCS_CUDA(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_THREADS), args, chol_smem_bytes(), st));
     return PCS_OK;
 }
 
