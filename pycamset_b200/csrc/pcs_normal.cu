@@ -325,7 +325,7 @@ __device__ __forceinline__ void stage_rows(const NeRows& R, double* __restrict__
 // stores, 8 = table rows made up from registers (no row loads), 16 = no segment flush.
 // (A variant with two observations per lane and loop trip -- two independent evaluation chains -- was measured at 0.177 ms
 // against 0.135 ms: the second observation's rows spill.  Removed.)
-template <int CTAS_PER_SM, int WARPS, int KO = 0>
+template <int CTAS_PER_SM, int WARPS, int KO = 0, bool PF_LATE = true>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
 k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __restrict__ s_cam, const int32_t* __restrict__ s_pose,
          const int32_t* __restrict__ s_key, const double2* __restrict__ s_uv, const int64_t* __restrict__ seg_start,
@@ -378,10 +378,15 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
     for (int64_t base = begin; base < end; base += 32) {
         const NeObs ob = nxt;
         NeRows rows;
-        load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);
+        if (!PF_LATE) load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);
         eval_rows<(KO & 8) != 0>(ob, camtab, posetab, pts, rows);
+        // PF_LATE: the next trip's stream loads are issued only now.  Issued at the top of the trip they shared a scoreboard
+        // with this trip's table-row loads, so the first use of a row waited for the whole DRAM latency of the prefetch
+        // (17 % of the warp samples sat on two such instructions); the Gram phase below is long enough to cover them:
+        // 131.1 -> 127.0 us at config 4 (a two-deep variant spills and gains nothing; PCS_NE_PF_LATE=0 restores the early issue).
+        if (PF_LATE) load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);
         // the next trip's pose rows (new for every segment) are pulled into L1 while this trip's Gram phase runs
-        if (nxt.m >= 0) {
+        if (!PF_LATE && nxt.m >= 0) {
             const double* nx = posetab + (int64_t)nxt.m * POSE_STRIDE;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
@@ -627,14 +632,9 @@ k_normal_mixed(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t*
     load_obs(nxt, begin + lane, end, s_cam, s_pose, s_key, s_uv);
     for (int64_t base = begin; base < end; base += 32) {
         const NeObs ob = nxt;
-        load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);
         NeRows R;
         eval_rows(ob, camtab, posetab, pts, R);
-        if (nxt.m >= 0) {
-            const double* nx = posetab + (int64_t)nxt.m * POSE_STRIDE;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 16));
-        }
+        load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);   // issued after the evaluation, as in k_normal
         const int cnt = (int)min((int64_t)32, end - base);
         const int c = ob.c, m = ob.m;
         if (lane < cnt) {
@@ -778,7 +778,7 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     const size_t smem = (size_t)warps * (mixed ? NEM_WARP_DOUBLES : NE_WARP_DOUBLES) * sizeof(double);
     auto kern_mixed = nem_ctas == 5 ? k_normal_mixed<5, 4> : k_normal_mixed<4, 4>;
     if (mixed) PCS_CUDA(ensure_dynamic_smem(kern_mixed, smem));
-    else PCS_CUDA(ensure_dynamic_smem(k_normal<5, 4>, smem));
+    else { PCS_CUDA(ensure_dynamic_smem(k_normal<5, 4>, smem)); PCS_CUDA(ensure_dynamic_smem(k_normal<5, 4, 0, false>, smem)); }
     // persistent-style grid: `ctas` CTAs of `warps` warps per SM; at least ~64 observations per warp
     const int64_t n_part_obs = p->N / n_parts + 1;
     int64_t n_warps = std::min<int64_t>((n_part_obs + 63) / 64, (int64_t)p->sm_count * ctas * warps);
@@ -788,7 +788,8 @@ int launch_normal_blocks(pcs_problem* p, bool targets_cleared, int part, int n_p
     const int tslot = (int)(p->timing_count % (int64_t)std::max<size_t>(p->ev_a.size(), 1));
     if (p->timing) PCS_CUDA(cudaEventRecord(p->ev_a[tslot], p->stream));
     const int64_t* ranges = p->warp_seg[n_parts > 1 ? 1 : 0] + (int64_t)part * (n_warps + 1);
-    auto kern_fp64 = k_normal<5, 4>;
+    static const bool pf_early = [] { const char* e = std::getenv("PCS_NE_PF_LATE"); return e && e[0] == '0'; }();   // A/B switch
+    auto kern_fp64 = pf_early ? k_normal<5, 4, 0, false> : k_normal<5, 4>;
 #ifdef PCS_NE_KNOCKOUT
     {
         static const int ko = [] { const char* e = std::getenv("PCS_NE_KO"); return e ? std::atoi(e) : 0; }();
