@@ -291,8 +291,8 @@ def lm_e2e_handlers(seed, real_reference, max_nfev):
 
 def lm_e2e_device(seed, device):
     """Device arm: pycamset_b200.handler.run_bundle_adjustment(handler) -- problem export + upload, device LM, result
-    read-back, residual / Jacobian at the solution -- timed by wall clock around the whole call (second call: the first
-    pays CUDA module loading and workspace allocation)."""
+    read-back, residual / Jacobian at the solution -- timed by wall clock around the whole call (best of three calls after
+    a warm-up call that pays CUDA module loading and workspace allocation)."""
     from pycamset_b200.handler import run_bundle_adjustment
     out, real = {}, True
     try:
@@ -307,9 +307,11 @@ def lm_e2e_device(seed, device):
     for name, h in lm_e2e_handlers(seed, real, budget):
         try:
             run_bundle_adjustment(h, device=device)    # warm-up
-            t0 = time.perf_counter()
-            res, _ = run_bundle_adjustment(h, device=device)
-            dt = time.perf_counter() - t0
+            dt = float("inf")
+            for _ in range(3):                         # best of three: the call is mostly host-side Python, the box is shared
+                t0 = time.perf_counter()
+                res, _ = run_bundle_adjustment(h, device=device)
+                dt = min(dt, time.perf_counter() - t0)
             st = res["lm"]
             out[name] = {"seconds": dt, "iterations": st["iterations"], "iter_per_s": st["iterations"] / dt,
                          "solve_seconds_device": st["seconds"], "status": st["status"], "cost_final": float(res.cost),

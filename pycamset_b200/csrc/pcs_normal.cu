@@ -383,7 +383,8 @@ k_normal(int n_warps, const int64_t* __restrict__ warp_seg, const int32_t* __res
         // PF_LATE: the next trip's stream loads are issued only now.  Issued at the top of the trip they shared a scoreboard
         // with this trip's table-row loads, so the first use of a row waited for the whole DRAM latency of the prefetch
         // (17 % of the warp samples sat on two such instructions); the Gram phase below is long enough to cover them:
-        // 131.1 -> 127.0 us at config 4 (a two-deep variant spills and gains nothing; PCS_NE_PF_LATE=0 restores the early issue).
+        // 131.1 -> 127.0 us at config 4 (a two-deep variant spills and gains nothing, nor does pulling the next trip's pose
+        // rows into L1 from pose indices loaded one trip further ahead; PCS_NE_PF_LATE=0 restores the early issue).
         if (PF_LATE) load_obs(nxt, base + 32 + lane, end, s_cam, s_pose, s_key, s_uv);
         // the next trip's pose rows (new for every segment) are pulled into L1 while this trip's Gram phase runs
         if (!PF_LATE && nxt.m >= 0) {
