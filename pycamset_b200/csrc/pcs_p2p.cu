@@ -26,6 +26,8 @@ struct P2PState {
     int rank = 0, world = 1;
     int64_t n = 0;          // doubles exchanged
     uint64_t epoch = 0;
+    bool sentinel = false;  // slots were handed over filled with the sentinel (pcs_p2p_allreduce_setup flags)
+    int* err = nullptr;     // device flag: a poll of the sentinel form timed out
 };
 
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
@@ -171,6 +173,109 @@ k_p2p_allreduce_multi(double* __restrict__ local, int64_t n, int rank, int world
     }
 }
 
+
+// "The data is the signal" form (default): the slots of a buffer hold a sentinel NaN whenever they are empty.  CTA b
+// pushes this rank's block into its slot at peer b -- no system fence, no flag -- and every CTA sums its 1 / world share of
+// the entries by polling the `world` slots of its OWN buffer until none of the values it needs is the sentinel (8-byte
+// stores are atomic, so a value is either the sentinel or complete), in rank order (identical bits on every rank), and
+// then puts the sentinel back.  A slot set is reused two exchanges later; the peer's write for that exchange causally
+// follows this rank's next push, which is issued by a later kernel of the same stream, i.e. after the reset below is
+// complete.  The result may only overwrite `local` once every CTA of this rank has finished reading it for its push:
+// a counter in the rank's own buffer (local traffic only).  Chain per exchange: one NVLink one-way trip + local polls.
+constexpr unsigned long long P2P_SENTINEL = 0x7ff8dead7ff8deadull;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const void* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void k_p2p_fill_sentinel(double* __restrict__ slots, int64_t n)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) reinterpret_cast<unsigned long long*>(slots)[i] = P2P_SENTINEL;
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(512)
+k_p2p_allreduce_sentinel(double* __restrict__ local, int64_t n, int rank, int world_rt, P2PPeers peers, uint64_t epoch, int* __restrict__ err)
+{
+    const int world = WORLD > 0 ? WORLD : world_rt;
+    const int tid = threadIdx.x, b = blockIdx.x;   // gridDim.x == world
+    const int64_t data = P2P_FLAG_DOUBLES + (int64_t)(epoch & 1) * world * n;
+    pdl_wait();
+    {
+        double* dst = peers.buf[b] + data + (int64_t)rank * n;
+        const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(local)) & 15) == 0;
+        const int64_t n2 = vec ? n / 2 : 0;
+        for (int64_t i0 = 0; i0 < n2; i0 += (int64_t)P2P_ILP * blockDim.x) {   // loads of a pass in flight together
+            double2 v[P2P_ILP];
+#pragma unroll
+            for (int u = 0; u < P2P_ILP; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+                if (i < n2) v[u] = reinterpret_cast<const double2*>(local)[i];
+            }
+#pragma unroll
+            for (int u = 0; u < P2P_ILP; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+                if (i < n2) reinterpret_cast<double2*>(dst)[i] = v[u];
+            }
+        }
+        for (int64_t i = 2 * n2 + tid; i < n; i += blockDim.x) dst[i] = local[i];
+    }
+    __syncthreads();
+    double* mine = peers.buf[rank];
+    unsigned long long* done = reinterpret_cast<unsigned long long*>(mine) + P2P_MAX_WORLD;
+    if (tid == 0) atomicAdd(done, 1ull);             // this CTA has finished reading `local`
+    const int64_t e0 = n * b / world, e1 = n * (b + 1) / world;
+    bool may_write = false;
+    for (int64_t i0 = e0; i0 < e1; i0 += (int64_t)P2P_SUM_ILP * blockDim.x) {
+        double s[P2P_SUM_ILP];
+#pragma unroll
+        for (int u = 0; u < P2P_SUM_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            s[u] = 0.0;
+            if (i < e1) {
+                unsigned long long v[WORLD > 0 ? WORLD : P2P_MAX_WORLD];
+                int spins = 0;
+                bool ready;
+                do {
+                    ready = true;
+#pragma unroll
+                    for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+                        if (r < world) {
+                            v[r] = ld_relaxed_sys_u64(mine + data + (int64_t)r * n + i);
+                            ready = ready && v[r] != P2P_SENTINEL;
+                        }
+                } while (!ready && ++spins < (1 << 24));
+                if (!ready) *err = 1;                // a peer never delivered: report instead of hanging
+#pragma unroll
+                for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+                    if (r < world) s[u] += __longlong_as_double((long long)v[r]);   // rank order: identical bits everywhere
+            }
+        }
+        if (!may_write) {                            // before the first result lands in `local`: all CTAs are done reading it
+            if (tid == 0) {
+                int spins = 0;
+                while (ld_relaxed_sys_u64(done) < epoch * (uint64_t)world && ++spins < (1 << 24)) { }
+            }
+            __syncthreads();
+            may_write = true;
+        }
+#pragma unroll
+        for (int u = 0; u < P2P_SUM_ILP; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x + tid;
+            if (i < e1) {
+                local[i] = s[u];
+#pragma unroll
+                for (int r = 0; r < (WORLD > 0 ? WORLD : P2P_MAX_WORLD); ++r)
+                    if (r < world) reinterpret_cast<unsigned long long*>(mine + data + (int64_t)r * n)[i] = P2P_SENTINEL;
+            }
+        }
+    }
+}
+
 }  // namespace pcs
 
 using namespace pcs;
@@ -199,6 +304,19 @@ int pcs_p2p_allreduce_setup(pcs_problem* p, int rank, int world, void* const* pe
         st->peers.buf[r] = (double*)peer_buffers[r];
     }
     st->rank = rank; st->world = world; st->n = (int64_t)p->C * 240 + 1; st->epoch = 0;
+    // the sentinel form needs the slots of THIS rank's buffer filled with the sentinel (done here; the caller's barrier
+    // after setup -- see pycamset_b200/distributed.py -- keeps any peer from pushing before that); PCS_P2P_SENTINEL=0
+    // selects the fence + flag protocol
+    const char* e = std::getenv("PCS_P2P_SENTINEL");
+    st->sentinel = !(e && e[0] == '0');
+    if (st->sentinel) {
+        if (!st->err) PCS_CUDA(cudaMalloc((void**)&st->err, sizeof(int)));
+        PCS_CUDA(cudaMemsetAsync(st->err, 0, sizeof(int), p->stream));
+        const int64_t n_slots = 2 * (int64_t)world * st->n;
+        k_p2p_fill_sentinel<<<(int)((n_slots + 255) / 256), 256, 0, p->stream>>>(st->peers.buf[rank] + P2P_FLAG_DOUBLES, n_slots);
+        PCS_CUDA(cudaGetLastError());
+        PCS_CUDA(cudaStreamSynchronize(p->stream));
+    }
     return PCS_OK;
 }
 
@@ -213,7 +331,11 @@ int pcs_p2p_allreduce_camera_blocks(pcs_problem* p)
     // worlds of 8 and more use the multi-CTA form (PCS_P2P_MULTI=0/1 forces either one for A/B runs)
     static const int force = [] { const char* e = std::getenv("PCS_P2P_MULTI"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     const bool multi = force >= 0 ? force == 1 : st->world >= 8;
-    if (multi) {
+    if (st->sentinel) {
+        auto sk = st->world == 2 ? k_p2p_allreduce_sentinel<2> : st->world == 4 ? k_p2p_allreduce_sentinel<4>
+                  : st->world == 8 ? k_p2p_allreduce_sentinel<8> : k_p2p_allreduce_sentinel<0>;
+        PCS_CUDA(launch_pdl(sk, dim3(st->world), dim3(512), 0, p->stream, p->U, st->n, st->rank, st->world, st->peers, st->epoch, st->err));
+    } else if (multi) {
         auto mk = st->world == 2 ? k_p2p_allreduce_multi<2> : st->world == 4 ? k_p2p_allreduce_multi<4>
                   : st->world == 8 ? k_p2p_allreduce_multi<8> : k_p2p_allreduce_multi<0>;
         PCS_CUDA(launch_pdl(mk, dim3(st->world), dim3(512), 0, p->stream, p->U, st->n, st->rank, st->world, st->peers, st->epoch));
@@ -230,6 +352,7 @@ int pcs_p2p_allreduce_camera_blocks(pcs_problem* p)
 namespace pcs {
 void p2p_free(pcs_problem* p)
 {
+    if (p->p2p && ((P2PState*)p->p2p)->err) cudaFree(((P2PState*)p->p2p)->err);
     delete (P2PState*)p->p2p;
     p->p2p = nullptr;
 }

@@ -118,6 +118,8 @@ class P2PCameraAllReduce:
         torch.cuda.synchronize(problem.device)
         dist.barrier(group)                       # every rank's flags are zero before anyone starts signalling
         problem.p2p_setup(self.rank, self.world, list(self.handle.buffer_ptrs), nbytes)
+        torch.cuda.synchronize(problem.device)
+        dist.barrier(group)                       # ... and every rank's slots hold the "empty" sentinel (filled by the setup call)
 
     def __call__(self):
         self.problem.p2p_allreduce_camera_blocks()
