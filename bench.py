@@ -560,6 +560,8 @@ def measure_workload(args, workload, rank, world, dev, stream, flush_buf, steps,
         dist.all_reduce(c)
         n_total = int(c.item())
     ms_per_step = total_ms / steps
+    if exch.kind == "p2p" and prob.p2p_timed_out():   # a poll gave up waiting for a peer: the sums (and the number) are invalid
+        exch.check = (exch.check or "") + "; TIMED OUT waiting for a peer"
     res.update(value=n_total / (ms_per_step * 1e-3) / 1e6, ms_per_step=ms_per_step, n_obs_total=n_total, n_obs_per_gpu=n_local,
                n_segments_per_gpu=prob.n_segments, n_free_per_gpu=prob.n_free, kernel_ms=float(np.mean(kern_ms)),
                gpu_launches=gpu_launches, clocks=clocks, setup_s=setup_s, wall_s_timed_region=wall_s,

@@ -192,11 +192,17 @@ PCS_API int pcs_gauge_scale(int device, int64_t n_points, const double* estimate
  * peer memory -- the only exchange step of a pose-sharded normal-equation evaluation (C * 240 + 1 doubles, latency
  * bound).  Every rank allocates a zero-initialised buffer of pcs_p2p_buffer_bytes(p, world) that all peers have mapped
  * (e.g. torch.distributed._symmetric_memory) and passes the world's pointers, own buffer at index `rank`.
- * pcs_p2p_allreduce_camera_blocks enqueues one kernel on the problem's stream (a single CTA, or one CTA per peer for
- * worlds of 8 and more); all ranks must call it the same number of times.  No reference counterpart (the reference is single-process). */
+ * pcs_p2p_allreduce_setup marks the slots of the rank's own buffer as empty (a sentinel NaN; the call synchronises the
+ * problem's stream) -- the caller must put a barrier across the ranks between the setup call and the first exchange.
+ * pcs_p2p_allreduce_camera_blocks enqueues one kernel (one CTA per peer) on the problem's stream: the rank's block is
+ * pushed into its slot at every peer without fence or flag, the arrival of the data is the signal (csrc/pcs_p2p.cu);
+ * all ranks must call it the same number of times.  PCS_P2P_SENTINEL=0 selects the older fence + flag protocol.
+ * pcs_p2p_status: *timed_out = 1 if a poll ever gave up waiting for a peer (the sums of that exchange are then
+ * invalid); synchronises the stream.  No reference counterpart (the reference is single-process). */
 PCS_API int64_t pcs_p2p_buffer_bytes(const pcs_problem* p, int world_size);
 PCS_API int pcs_p2p_allreduce_setup(pcs_problem* p, int rank, int world_size, void* const* peer_buffers, int64_t buffer_bytes);
 PCS_API int pcs_p2p_allreduce_camera_blocks(pcs_problem* p);
+PCS_API int pcs_p2p_status(pcs_problem* p, int* timed_out);
 
 /* Levenberg-Marquardt on the device (replaces scipy.optimize.least_squares TRF + LSMR as driven by
  * run_bundle_adjustment, optimisation_handling.py:52-117). */

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pcs_csr_structure", "pcs_jacobian_values", "pcs_jacobian_values_dev", "pcs_segments", "pcs_normal_equations",
     "pcs_normal_equations_dev", "pcs_point_blocks", "pcs_normal_dense", "pcs_device_buffers_get", "pcs_set_allreduce",
     "pcs_lm_default_options", "pcs_lm_solve", "pcs_spd_solve", "pcs_syrk_sub", "pcs_lm_schur_fraction", "pcs_timing_enable", "pcs_timing_get", "pcs_timing_get_all", "pcs_launch_count",
-    "pcs_costfn", "pcs_gauge_scale", "pcs_set_normal_precision", "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_device_sm_count",
+    "pcs_costfn", "pcs_gauge_scale", "pcs_set_normal_precision", "pcs_p2p_buffer_bytes", "pcs_p2p_allreduce_setup", "pcs_p2p_allreduce_camera_blocks", "pcs_p2p_status", "pcs_device_sm_count",
     "pcs_version",
 ]
 
@@ -123,6 +123,7 @@ def load() -> ct.CDLL:
     lib.pcs_gauge_scale.argtypes = [ct.c_int, ct.c_int64, vp, vp, vp, ct.c_double, ct.c_double, ct.c_double, ct.POINTER(ct.c_double), ct.POINTER(ct.c_int64)]
     lib.pcs_costfn.argtypes = [vp, ct.c_int, vp, vp, vp, vp, vp, vp]
     lib.pcs_p2p_buffer_bytes.argtypes = [vp, ct.c_int]
+    lib.pcs_p2p_status.argtypes = [vp, ct.POINTER(ct.c_int)]
     lib.pcs_p2p_buffer_bytes.restype = ct.c_int64
     lib.pcs_p2p_allreduce_setup.argtypes = [vp, ct.c_int, ct.c_int, ct.POINTER(vp), ct.c_int64]
     lib.pcs_p2p_allreduce_camera_blocks.argtypes = [vp]

@@ -347,6 +347,19 @@ int pcs_p2p_allreduce_camera_blocks(pcs_problem* p)
     return PCS_OK;
 }
 
+int pcs_p2p_status(pcs_problem* p, int* timed_out)
+{
+    PCS_REQUIRE(p && p->p2p && timed_out, "NULL argument or pcs_p2p_allreduce_setup has not been called");
+    PCS_CUDA(cudaSetDevice(p->device));
+    P2PState* st = (P2PState*)p->p2p;
+    *timed_out = 0;
+    if (st->err) {
+        PCS_CUDA(cudaMemcpyAsync(timed_out, st->err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        PCS_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    return PCS_OK;
+}
+
 }  // extern "C"
 
 namespace pcs {

@@ -279,6 +279,12 @@ class BundleProblem:
     def p2p_allreduce_camera_blocks(self):
         L.check(self._lib.pcs_p2p_allreduce_camera_blocks(self._h))
 
+    def p2p_timed_out(self) -> bool:
+        """True if a poll of the peer-memory exchange ever gave up waiting for a peer (synchronises the stream)."""
+        f = ct.c_int()
+        L.check(self._lib.pcs_p2p_status(self._h, ct.byref(f)))
+        return bool(f.value)
+
     def set_allreduce(self, fn, rank, world_size):
         """fn(ptr:int, n:int, op:int, stream:int) -> None; installed as the multi-GPU combine hook of the LM solver."""
         def _cb(user, buf, n, op, stream):
