@@ -40,6 +40,12 @@ struct LmWorkspace {
     double* y = nullptr;     // [M][6]  L^-1 b_p
     double* Z = nullptr;     // [np][nc] column-major (nc rows): W L^-T scattered by (camera, pose)
     SchurPlan plan;          // static block sparsity of Z: pose column order + non-zero (tile, slab) units (pcs_schur.cu)
+    // self-calibration chain with more point than pose unknowns (3 K > 6 M): the POINTS are eliminated (3 x 3 blocks) and
+    // the reduced system is over cameras + poses (15 C + 6 M) instead of cameras + points -- 162 instead of 1503 unknowns
+    // on the reference's ccube fixture.  L / y then hold the point factors [K][9] / [K][3], Z is [3 K][nc].
+    bool pts_elim = false;
+    int32_t* seg_of = nullptr;   // [C][M] segment of (camera, pose) or -1 (placement of the W blocks in the reduced system)
+    double* dck = nullptr;       // [15 C + 3 K] camera + point part of the step, in the layout k_lm_assemble_delta reads
     double* red = nullptr;   // [S nc*nc | rhs nc | gc nc | cost 1]  (all-reduce unit)
     int64_t red_doubles = 0;
     double* delta = nullptr; // [Lparams]
@@ -287,6 +293,197 @@ k_lm_point_Z(int M, int K, int64_t nc, int64_t row0, const double* __restrict__ 
     if (dot != 0.0) atomicAdd(rhs + row, -dot);
 }
 
+// ---- point elimination (self-calibration chain, 3 K > 6 M) ------------------------------------------------------------
+__global__ void k_seg_of(int64_t S, int M, const int32_t* __restrict__ seg_cam, const int32_t* __restrict__ seg_pose, int32_t* __restrict__ seg_of)
+{
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s < S) seg_of[(int64_t)seg_cam[s] * M + seg_pose[s]] = (int32_t)s;
+}
+
+// per point: Cholesky of the damped, masked 3 x 3 block, y = L^-1 (-g); fixed / unobserved coordinates are identity rows
+__global__ void k_lm_point_factor(int K, double lambda, const double* __restrict__ Pk, const double* __restrict__ gk,
+                                  const uint8_t* __restrict__ key_mask, double* __restrict__ Lout, double* __restrict__ yout,
+                                  double* __restrict__ scal)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const unsigned mask = key_mask[k];
+    double A[3][3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const bool fi = mask & (1u << i);
+        b[i] = fi ? -gk[3 * (int64_t)k + i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const bool fj = mask & (1u << j);
+            double v = (fi && fj) ? Pk[(int64_t)k * 9 + i * 3 + j] : 0.0;
+            if (i == j) v = (fi && v > 0.0) ? v + lambda * v : 1.0;
+            A[i][j] = v;
+        }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double d = A[j][j];
+#pragma unroll
+        for (int q = 0; q < j; ++q) d -= A[j][q] * A[j][q];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        d = sqrt(d);
+        A[j][j] = d;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < 3; ++i) {
+            double s = A[i][j];
+#pragma unroll
+            for (int q = 0; q < j; ++q) s -= A[i][q] * A[j][q];
+            A[i][j] = s * inv;
+        }
+    }
+    if (!ok) scal[5] = 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double s = b[i];
+#pragma unroll
+        for (int q = 0; q < i; ++q) s -= A[i][q] * b[q];
+        b[i] = s / A[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        yout[3 * (int64_t)k + i] = b[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Lout[(int64_t)k * 9 + i * 3 + j] = (j <= i) ? A[i][j] : 0.0;
+    }
+}
+
+// S = [[U + lambda D, .], [W^T, V + lambda D]] over cameras + poses (lower triangle, every entry written once), masked;
+// rhs = -g, g copy; clears the step scalars and the factorisation status (as k_lm_init_reduced does)
+__global__ void k_lm_init_reduced_cp(int C, int M, int64_t nc, int64_t nl, double lambda, const double* __restrict__ U,
+                                     const double* __restrict__ gc, const double* __restrict__ V, const double* __restrict__ gp,
+                                     const double* __restrict__ W, const int32_t* __restrict__ seg_of, const double* __restrict__ cost,
+                                     const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask,
+                                     double* __restrict__ Smat, double* __restrict__ rhs, double* __restrict__ gcopy,
+                                     double* __restrict__ cost_out, double* __restrict__ scal, int* __restrict__ info)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < 8) scal[t] = 0.0;
+    if (t == 8) { *info = 0; *cost_out = *cost; }
+    if (t >= nc * nc) return;
+    const int64_t col = t / nc, row = t % nc;      // column-major S
+    const int64_t n_cam = 15 * (int64_t)C;
+    double v = 0.0;
+    if (row >= nl || col >= nl) {
+        if (row == col) { rhs[row] = 0.0; gcopy[row] = 0.0; }
+    } else if (row < n_cam && col < n_cam) {
+        const int c = (int)(row / 15), a = (int)(row % 15), cb = (int)(col / 15), b = (int)(col % 15);
+        if (c == cb) {
+            const unsigned mask = cam_mask[c];
+            const bool fa = mask & (1u << a), fb = mask & (1u << b);
+            v = (fa && fb) ? U[(int64_t)c * 225 + a * 15 + b] : 0.0;
+            if (a == b) {
+                v = fa ? v + lambda * v : 0.0;
+                rhs[row] = fa ? -gc[row] : 0.0;
+                gcopy[row] = fa ? gc[row] : 0.0;
+            }
+        }
+    } else if (row >= n_cam && col >= n_cam) {
+        const int64_t jr = row - n_cam, jc = col - n_cam;
+        const int m = (int)(jr / 6), a = (int)(jr % 6), mb = (int)(jc / 6), b = (int)(jc % 6);
+        if (m == mb) {
+            const unsigned mask = pose_mask[m];
+            const bool fa = mask & (1u << a), fb = mask & (1u << b);
+            v = (fa && fb) ? V[(int64_t)m * 36 + a * 6 + b] : 0.0;
+            if (a == b) {
+                v = fa ? v + lambda * v : 0.0;
+                rhs[row] = fa ? -gp[jr] : 0.0;
+                gcopy[row] = fa ? gp[jr] : 0.0;
+            }
+        }
+    } else if (row >= n_cam) {   // pose row, camera column: W_s[a][j]
+        const int64_t jr = row - n_cam;
+        const int m = (int)(jr / 6), j = (int)(jr % 6), c = (int)(col / 15), a = (int)(col % 15);
+        const int32_t s = seg_of[(int64_t)c * M + m];
+        if (s >= 0 && (pose_mask[m] & (1u << j)) && (cam_mask[c] & (1u << a))) v = W[(int64_t)s * 90 + a * 6 + j];
+    }
+    Smat[t] = v;
+}
+
+// Z rows of the point elimination: for reduced row r (camera or pose unknown) and point k, z = x L_k^-T with x the 1 x 3
+// coupling block row (Xck / Ymk), written to the dense column-major Z [3 K][nc]; rhs[r] -= z . y_k.  A thread handles one
+// row and PT_CHUNK consecutive points (one reduction per thread, consecutive rows in consecutive lanes).
+constexpr int PT_CHUNK = 16;
+__global__ void __launch_bounds__(128)
+k_lm_point_elim_Z(int C, int M, int K, int64_t nc, int64_t nl, const double* __restrict__ Xck, const double* __restrict__ Ymk,
+                  const double* __restrict__ L, const double* __restrict__ y, const uint16_t* __restrict__ cam_mask,
+                  const uint8_t* __restrict__ pose_mask, const uint8_t* __restrict__ key_mask, double* __restrict__ Z,
+                  double* __restrict__ rhs)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int k0 = blockIdx.y * PT_CHUNK;
+    if (r >= nc) return;
+    const int64_t n_cam = 15 * (int64_t)C;
+    const bool is_cam = r < n_cam, live = r < nl;
+    int blk = 0, a = 0;
+    bool row_free = false;
+    if (live) {
+        if (is_cam) { blk = (int)(r / 15); a = (int)(r % 15); row_free = cam_mask[blk] & (1u << a); }
+        else { blk = (int)((r - n_cam) / 6); a = (int)((r - n_cam) % 6); row_free = pose_mask[blk] & (1u << a); }
+    }
+    double dot = 0.0;
+    for (int k = k0; k < min(K, k0 + PT_CHUNK); ++k) {
+        double z[3] = {0.0, 0.0, 0.0};
+        if (row_free) {
+            const double* x = is_cam ? Xck + (((int64_t)blk * K + k) * 15 + a) * 3 : Ymk + (((int64_t)blk * K + k) * 6 + a) * 3;
+            const unsigned km = key_mask[k];
+            const double* Lk = L + (int64_t)k * 9;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double v = (km & (1u << i)) ? x[i] : 0.0;
+#pragma unroll
+                for (int q = 0; q < i; ++q) v -= Lk[i * 3 + q] * z[q];
+                z[i] = v / Lk[i * 3 + i];
+                dot = fma(z[i], y[3 * (int64_t)k + i], dot);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Z[(3 * (int64_t)k + i) * nc + r] = z[i];   // every entry is written: no memset
+    }
+    if (dot != 0.0) atomicAdd(rhs + r, -dot);
+}
+
+// delta_k = L_k^-T (y_k - Z_k^T delta_r), one warp per point; written behind the camera part of `dck`
+__global__ void __launch_bounds__(128)
+k_lm_point_back(int K, int64_t nc, const double* __restrict__ L, const double* __restrict__ y, const double* __restrict__ Z,
+                const double* __restrict__ delta_r, double* __restrict__ delta_k)
+{
+    const int k = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (k >= K) return;
+    double t[3] = {0.0, 0.0, 0.0};
+    const double* Zk = Z + 3 * (int64_t)k * nc;
+    for (int64_t r = lane; r < nc; r += 32) {
+        const double d = delta_r[r];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) t[i] = fma(Zk[i * nc + r], d, t[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[i] += __shfl_xor_sync(0xffffffffu, t[i], o);
+    if (lane != 0) return;
+    const double* Lk = L + (int64_t)k * 9;
+    double v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = y[3 * (int64_t)k + i] - t[i];
+#pragma unroll
+    for (int i = 2; i >= 0; --i) {
+        double s = v[i];
+#pragma unroll
+        for (int q = i + 1; q < 3; ++q) s -= Lk[q * 3 + i] * v[q];
+        v[i] = s / Lk[i * 3 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) delta_k[3 * (int64_t)k + i] = v[i];
+}
+
 // rows whose diagonal is exactly zero after the reduction (fixed, or unobserved by every rank) -> identity
 __global__ void k_lm_fix_diag(int64_t nc, double* __restrict__ Smat)
 {
@@ -338,7 +535,7 @@ __global__ void k_lm_assemble_delta(int C, int M, int K3, double lambda, const d
                                     const double* __restrict__ gp, const double* __restrict__ Pk, const double* __restrict__ gk,
                                     const uint16_t* __restrict__ cam_mask, const uint8_t* __restrict__ pose_mask,
                                     const uint8_t* __restrict__ key_mask, const double* __restrict__ params,
-                                    double* __restrict__ delta, double* __restrict__ scal, int rank0)
+                                    double* __restrict__ delta, double* __restrict__ scal, int rank0, int pts_ginf)
 {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t n_cam = 15 * (int64_t)C, n_pose = 6 * (int64_t)M;
@@ -372,6 +569,7 @@ __global__ void k_lm_assemble_delta(int C, int M, int K3, double lambda, const d
             D = f ? Pk[(int64_t)k * 9 + a * 4] : 0.0;
             g = f ? gk[j] : 0.0;
             replicated = true;
+            if (pts_ginf) ginf = fabs(g);   // point elimination: the point gradient is not part of the reduced copy
         }
         delta[t] = d;
         pred = d * (lambda * D * d - g);
@@ -379,7 +577,7 @@ __global__ void k_lm_assemble_delta(int C, int M, int K3, double lambda, const d
             dx2 = d * d;
             x2 = params[t] * params[t];
         }
-        ginf = replicated ? 0.0 : fabs(g);  // the replicated gradient norm is taken from the all-reduced copy (k_lm_take_step)
+        if (!replicated) ginf = fabs(g);  // the replicated gradient norm is taken from the all-reduced copy (k_lm_take_step)
     }
     // block reduction
     __shared__ double sh[4][8];
@@ -534,6 +732,8 @@ void lm_free(pcs_problem* p)
     if (w->blas) cublasDestroy(w->blas);
     if (w->solver) cusolverDnDestroy(w->solver);
     schur_plan_free(&w->plan);
+    if (w->seg_of) cudaFree(w->seg_of);
+    if (w->dck) cudaFree(w->dck);
     double* ptrs[] = {w->L, w->y, w->Z, w->red, w->delta, w->backup, w->scal, w->work, w->Hd, w->rhs, w->Ldiag, w->ne_alt};
     for (double* q : ptrs) if (q) cudaFree(q);
     if (w->info) cudaFree(w->info);
@@ -594,16 +794,34 @@ static int lm_prepare_impl(pcs_problem* p, LmWorkspace* w)
     // PCS_LM_SELFCAL=dense forces the dense fallback of the self-calibration chain (A/B runs, tests)
     static const bool force_dense = [] { const char* e = std::getenv("PCS_LM_SELFCAL"); return e && e[0] == 'd'; }();
     if (p->chain == PCS_CHAIN_TEMPLATE || (p->Pk && !force_dense)) {
-        w->nl = 15 * (int64_t)p->C + (p->chain == PCS_CHAIN_SELFCAL ? 3 * (int64_t)p->K : 0);   // cameras (+ target points)
+        // Which block set is eliminated.  Template chain: the poses.  Self-calibration chain: poses AND points are block
+        // diagonal but coupled to each other, so only one of them can go; the larger one does (3 K point unknowns against
+        // 6 M pose unknowns; PCS_LM_SELFCAL=poses forces the pose elimination for A/B runs and tests).  The point
+        // elimination is single-rank: its reduced system contains the (rank-local) poses.
+        const char* em = std::getenv("PCS_LM_SELFCAL");
+        w->pts_elim = p->chain == PCS_CHAIN_SELFCAL && p->world == 1 && 3 * (int64_t)p->K > 6 * (int64_t)p->M && !(em && em[0] == 'p');
+        if (w->pts_elim) {
+            w->nl = 15 * (int64_t)p->C + 6 * (int64_t)p->M;       // cameras + poses
+            w->np = 3 * (int64_t)p->K;                            // eliminated: point coordinates
+        } else {
+            w->nl = 15 * (int64_t)p->C + (p->chain == PCS_CHAIN_SELFCAL ? 3 * (int64_t)p->K : 0);   // cameras (+ target points)
+            w->np = 6 * (int64_t)p->M;
+        }
         w->nc = (w->nl + 31) / 32 * 32;
-        w->np = 6 * (int64_t)p->M;
-        PCS_CUDA(cudaMalloc((void**)&w->L, (size_t)p->M * 36 * 8));
+        PCS_CUDA(cudaMalloc((void**)&w->L, (size_t)(w->pts_elim ? (int64_t)p->K * 9 : (int64_t)p->M * 36) * 8));
         PCS_CUDA(cudaMalloc((void**)&w->y, (size_t)w->np * 8));
         PCS_CUDA(cudaMalloc((void**)&w->Z, (size_t)(w->nc * w->np) * 8));
         PCS_CUDA(cudaMemsetAsync(w->Z, 0, (size_t)(w->nc * w->np) * 8, p->stream));  // sparsity pattern is static
+        if (w->pts_elim) {
+            PCS_CUDA(cudaMalloc((void**)&w->seg_of, (size_t)p->C * p->M * sizeof(int32_t)));
+            PCS_CUDA(cudaMemsetAsync(w->seg_of, 0xff, (size_t)p->C * p->M * sizeof(int32_t), p->stream));
+            if (p->n_seg) k_seg_of<<<grid_for(p->n_seg, 256), 256, 0, p->stream>>>(p->n_seg, p->M, p->seg_cam, p->seg_pose, w->seg_of);
+            PCS_CUDA(cudaGetLastError());
+            PCS_CUDA(cudaMalloc((void**)&w->dck, (size_t)(15 * (int64_t)p->C + 3 * (int64_t)p->K) * 8));
+        }
         // block-sparse pose elimination (PCS_LM_SCHUR=dense: full iteration space, identity column order -- A/B runs, tests)
         const char* es = std::getenv("PCS_LM_SCHUR");
-        if (!(es && es[0] == 'd')) PCS_TRY(schur_plan_build(p, w->nc, w->nl, &w->plan));
+        if (!w->pts_elim && !(es && es[0] == 'd')) PCS_TRY(schur_plan_build(p, w->nc, w->nl, &w->plan));
         w->red_doubles = w->nc * w->nc + 2 * w->nc + 1;
         PCS_CUDA(cudaMalloc((void**)&w->red, (size_t)w->red_doubles * 8));
         // own persistent Cholesky solve (PCS_LM_CHOL=cusolver selects the library path for A/B runs)
@@ -635,6 +853,42 @@ static int eval_normal(pcs_problem* p)
     PCS_TRY(launch_prepare(p, false, nullptr, p->ne, ne_zero_doubles(p)));
     PCS_TRY(launch_normal_blocks(p, true));
     if (p->chain == PCS_CHAIN_SELFCAL) PCS_TRY(launch_point_blocks(p));
+    return PCS_OK;
+}
+
+// Self-calibration chain, points eliminated (w->pts_elim): same contract as solve_template below.
+static int solve_points_eliminated(pcs_problem* p, LmWorkspace* w, double lambda)
+{
+    cudaStream_t st = p->stream;
+    const int64_t nc = w->nc, np = w->np, n_cam = 15 * (int64_t)p->C;
+    double* Smat = w->red;
+    double* rhs = w->red + nc * nc;
+    double* gcopy = rhs + nc;
+    double* cost_r = gcopy + nc;
+    k_lm_init_reduced_cp<<<grid_for(std::max<int64_t>(nc * nc, 9), 256), 256, 0, st>>>(p->C, p->M, nc, w->nl, lambda, p->U, p->gc, p->V, p->gp, p->W,
+                                                                                     w->seg_of, p->cost, p->cam_mask, p->pose_mask, Smat, rhs,
+                                                                                     gcopy, cost_r, w->scal, w->info);
+    k_lm_point_factor<<<grid_for(p->K, 128), 128, 0, st>>>(p->K, lambda, p->Pk, p->gk, p->key_mask, w->L, w->y, w->scal);
+    k_lm_point_elim_Z<<<dim3(grid_for(nc, 128), (p->K + PT_CHUNK - 1) / PT_CHUNK), 128, 0, st>>>(p->C, p->M, p->K, nc, w->nl, p->Xck, p->Ymk, w->L,
+                                                                                              w->y, p->cam_mask, p->pose_mask, p->key_mask, w->Z, rhs);
+    PCS_CUDA(cudaGetLastError());
+    PCS_TRY(launch_schur_syrk(st, p->sm_count, nc, np, w->Z, Smat, nullptr));
+    k_lm_fix_diag<<<grid_for(nc, 256), 256, 0, st>>>(nc, Smat);
+    if (w->chol_grid > 0) {
+        PCS_TRY(launch_chol_solve(st, w->chol_grid, nc, Smat, nc, rhs, w->Ldiag, w->bar, &w->bar_base, w->info));
+    } else {
+        PCS_SOLVER(cusolverDnDpotrf(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, Smat, (int)nc, w->work, w->lwork, w->info));
+        PCS_SOLVER(cusolverDnDpotrs(w->solver, CUBLAS_FILL_MODE_LOWER, (int)nc, 1, Smat, (int)nc, rhs, (int)nc, w->info));
+    }
+    p->n_launches += 7;
+    // rhs now holds [delta_c | delta_m]; the points follow from the back substitution
+    PCS_CUDA(cudaMemcpyAsync(w->dck, rhs, (size_t)n_cam * 8, cudaMemcpyDeviceToDevice, st));
+    k_lm_point_back<<<grid_for((int64_t)p->K * 32, 128), 128, 0, st>>>(p->K, nc, w->L, w->y, w->Z, rhs, w->dck + n_cam);
+    const int K3 = 3 * p->K;
+    k_lm_assemble_delta<<<grid_for(n_cam + 6 * (int64_t)p->M + K3, 128), 128, 0, st>>>(
+        p->C, p->M, K3, lambda, w->dck, rhs + n_cam, p->U, p->gc, p->V, p->gp, p->Pk, p->gk, p->cam_mask, p->pose_mask, p->key_mask, p->params,
+        w->delta, w->scal, 1, 1);
+    PCS_CUDA(cudaGetLastError());
     return PCS_OK;
 }
 
@@ -684,7 +938,7 @@ static int solve_template(pcs_problem* p, LmWorkspace* w, double lambda)
     const int K3 = selfcal ? 3 * p->K : 0;
     k_lm_assemble_delta<<<grid_for(15 * (int64_t)p->C + 6 * (int64_t)p->M + K3, 128), 128, 0, st>>>(
         p->C, p->M, K3, lambda, rhs, dp, p->U, p->gc, p->V, p->gp, p->Pk, p->gk, p->cam_mask, p->pose_mask, p->key_mask, p->params,
-        w->delta, w->scal, p->rank == 0);
+        w->delta, w->scal, p->rank == 0, 0);
     PCS_CUDA(cudaGetLastError());
     return PCS_OK;   // multi-rank: pred, |dx|^2, |x|^2 and the pose gradient norm are still rank-local here (k_lm_pack_scalars)
 }
@@ -722,6 +976,10 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
         return PCS_ERR_UNSUPPORTED;
     }
     PCS_TRY(lm_prepare(p));
+    if (((LmWorkspace*)p->lm_ws)->pts_elim && p->world > 1) {   // the all-reduce hook was installed after the workspace was built
+        lm_free(p);
+        PCS_TRY(lm_prepare(p));
+    }
     LmWorkspace* w = (LmWorkspace*)p->lm_ws;
     cudaStream_t st = p->stream;
     cudaEvent_t ev0 = w->ev0, ev1 = w->ev1;
@@ -762,7 +1020,7 @@ static int lm_solve_impl(pcs_problem* p, const double* x0, const pcs_lm_options*
             // normal-equation kernel (into the second output set) are enqueued back to back and read with ONE
             // synchronisation per iteration.  An accepted step already has its linearisation; a rejected one only
             // costs the difference between the full kernel and a residual-only pass.
-            rc = solve_template(p, w, lambda);
+            rc = w->pts_elim ? solve_points_eliminated(p, w, lambda) : solve_template(p, w, lambda);
             if (rc != PCS_OK) break;
             double* gcopy = w->red + w->nc * w->nc + w->nc;
             k_lm_take_step<<<grid_for(std::max<int64_t>(p->L, w->nc), 256), 256, 0, st>>>(p->L, w->nc, w->delta, p->params, w->backup,

@@ -3,8 +3,9 @@ free_point; BASELINE.json config 3, standard_bundle_handler.py:129-226).
 
   * every block -- U, V, W, g_c, g_m, r.r and the point blocks Pk, gk, Xck (camera x point), Ymk (pose x point) -- against
     the corresponding block of the oracle's dense J^T J / J^T r with no parameter fixed (tolerance 1e-9 sqrt(d_a d_b));
-  * the device LM on the block path (poses eliminated, cameras + points in the reduced system, own SYRK + Cholesky
-    kernels) against the dense n_free x n_free path (cuSOLVER), which stays as the comparator: same cost trajectory."""
+  * the device LM on the block path, in both elimination orders (points eliminated, cameras + poses in the reduced system
+    -- the library's choice when 3 K > 6 M; or poses eliminated, cameras + points in the reduced system), own SYRK +
+    Cholesky kernels, against the dense n_free x n_free path (cuSOLVER), which stays as the comparator: same cost trajectory."""
 import os
 import subprocess
 import sys
@@ -84,12 +85,14 @@ print("RESULT" + json.dumps(out))
 """
 
 
-def _run_child(case, dense):
+def _run_child(case, mode):
+    """mode: None = the library's choice (the larger of the pose / point block sets is eliminated), "poses" = pose
+    elimination forced (cameras + points in the reduced system), "dense" = the dense n_free x n_free comparator."""
     import json
     env = dict(os.environ)
     env.pop("PCS_LM_SELFCAL", None)
-    if dense:
-        env["PCS_LM_SELFCAL"] = "dense"
+    if mode:
+        env["PCS_LM_SELFCAL"] = mode
     pr = subprocess.run([sys.executable, "-c", _CHILD.format(root=str(ROOT), case=case)], capture_output=True, text=True, env=env,
                         timeout=600)
     assert pr.returncode == 0, pr.stderr[-2000:]
@@ -99,12 +102,14 @@ def _run_child(case, dense):
 @pytest.mark.parametrize("case", CASES)
 def test_selfcal_block_lm_matches_the_dense_path(case):
     """The library picks the path once per process (PCS_LM_SELFCAL), so each arm runs in its own interpreter."""
-    blk, dns = _run_child(case, False), _run_child(case, True)
-    for b, d in zip(blk[:3], dns[:3]):       # the first iterations: same linear systems, solved two ways
-        assert b["it"] == d["it"]
-        assert abs(b["cost"] - d["cost"]) <= 1e-8 * d["cost"], (b, d)
-    for b in blk:
-        assert abs(b["cost"] - b["true_cost"]) <= 1e-9 * b["true_cost"]
-    assert abs(blk[-1]["cost"] - dns[-1]["cost"]) <= 1e-3 * dns[-1]["cost"], (blk[-1], dns[-1])
-    if case == "ccube_selfcal":
-        assert blk[-1]["px"] < 0.2184        # the reference's own final error on this fixture (0.21834 px, max_nfev = 100)
+    dns = _run_child(case, "dense")
+    for mode in (None, "poses"):             # both elimination orders of the block path: the same Newton systems, solved differently
+        blk = _run_child(case, mode)
+        for b, d in zip(blk[:3], dns[:3]):   # the first iterations: same linear systems, solved two ways
+            assert b["it"] == d["it"]
+            assert abs(b["cost"] - d["cost"]) <= 1e-8 * d["cost"], (mode, b, d)
+        for b in blk:
+            assert abs(b["cost"] - b["true_cost"]) <= 1e-9 * b["true_cost"]
+        assert abs(blk[-1]["cost"] - dns[-1]["cost"]) <= 1e-3 * dns[-1]["cost"], (mode, blk[-1], dns[-1])
+        if case == "ccube_selfcal":
+            assert blk[-1]["px"] < 0.2184    # the reference's own final error on this fixture (0.21834 px, max_nfev = 100)
