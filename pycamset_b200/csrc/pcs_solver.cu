@@ -410,7 +410,7 @@ __global__ void k_lm_init_reduced_cp(int C, int M, int64_t nc, int64_t nl, doubl
 // Z rows of the point elimination: for reduced row r (camera or pose unknown) and point k, z = x L_k^-T with x the 1 x 3
 // coupling block row (Xck / Ymk), written to the dense column-major Z [3 K][nc]; rhs[r] -= z . y_k.  A thread handles one
 // row and PT_CHUNK consecutive points (one reduction per thread, consecutive rows in consecutive lanes).
-constexpr int PT_CHUNK = 16;
+constexpr int PT_CHUNK = 4;
 __global__ void __launch_bounds__(128)
 k_lm_point_elim_Z(int C, int M, int K, int64_t nc, int64_t nl, const double* __restrict__ Xck, const double* __restrict__ Ymk,
                   const double* __restrict__ L, const double* __restrict__ y, const uint16_t* __restrict__ cam_mask,
