@@ -561,7 +561,10 @@ int chol_prepare(int device, int64_t n, double** Ldiag, unsigned long long** bar
     int per_sm = 0;
     PCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_solve, CHOL_THREADS, smem));
     if (per_sm < 1) return PCS_OK;
-    const int n_tiles0 = nb + nb * (nb + 1) / 2;   // upper bound of the tiles of a phase
+    // work units of the widest phase: nb panel tiles + the 2 x 2 groups of the trailing tiles.  A grid wider than that only
+    // makes the barrier slower (every CTA arrives on one counter)
+    const int n_pairs0 = (nb + 1) / 2;
+    const int n_tiles0 = nb + n_pairs0 * (n_pairs0 + 1) / 2;
     // diagonal-block factors, followed by the mailbox of the back substitution (nb x 32 doubles, reset by every launch)
     PCS_CUDA(cudaMalloc((void**)Ldiag, ((size_t)nb * TB * TB + (size_t)nb * TB) * sizeof(double)));
     PCS_CUDA(cudaMalloc((void**)bar, sizeof(unsigned long long)));
