@@ -186,14 +186,25 @@ def make_optimisation_function(param_handler, threads: int = 1, device: int = 0)
     return gpu.make_loss_fun(threads), gpu.make_loss_jac(threads), init_params
 
 
+JAC_AUTO_LIMIT_BYTES = 2 << 30   # jac="auto": the explicit CSR Jacobian is formed at the solution only below this size
+
+
 def run_bundle_adjustment(param_handler, threads: int = 1, device: int = 0, solver: str = "lm", ftol=1e-8, xtol=1e-8,
-                          gtol=1e-8):
+                          gtol=1e-8, jac="auto"):
     """Drop-in for optimisation_handling.run_bundle_adjustment (:52-117): returns (result, camset).
 
     solver="lm"    Levenberg-Marquardt on the device (block normal equations + Schur complement).
     solver="scipy" scipy.optimize.least_squares driven by the CUDA closures, i.e. the reference's own solver
                    (TRF + LSMR, x_scale='jac', max_nfev from the handler) with only the callbacks replaced.
-    `result` carries x, fun, jac, cost, nfev, status like scipy's OptimizeResult."""
+    `result` carries x, fun, jac, cost, nfev, status like scipy's OptimizeResult.
+
+    jac (solver="lm"): the device solver never forms the Jacobian; `result.jac` is evaluated once at the solution because
+    the reference stores it with the camera set (camera_set.py:700-703) and writes it to the .camset file
+    (utils/saving.py:143-147).  At 10^8 observations that matrix is tens of GB, so: True = always,
+    False = never, "auto" = only below JAC_AUTO_LIMIT_BYTES of CSR values.  When it is skipped `result.jac` is None (the
+    reference's save_camset then omits it, as it does for any result without a usable Jacobian) and
+    `result.normal_blocks` holds the block diagonal of J^T J at the solution instead -- U [C][15][15], V [M][6][6], gc,
+    gp, cost: O(C + M) numbers."""
     gpu = param_handler if isinstance(param_handler, GpuBundleHandler) else GpuBundleHandler(param_handler, device=device)
     handler = gpu.handler
     loss_fn, jac_fn = gpu.make_loss_fun(threads), gpu.make_loss_jac(threads)
@@ -214,9 +225,13 @@ def run_bundle_adjustment(param_handler, threads: int = 1, device: int = 0, solv
     elif solver == "lm":
         x, st = gpu.solve(x0, max_nfev=max_nfev, ftol=ftol, xtol=xtol, gtol=gtol, verbose=1 if opts.get("verbosity", 0) > 1 else 0)
         fun = loss_fn(x)
-        result = OptimizeResult(x=x, fun=fun, jac=jac_fn(x), cost=0.5 * float(fun @ fun), nfev=st["n_eval_normal"] + st["n_eval_cost"],
-                                njev=st["n_eval_normal"], status=st["status"], success=st["status"] > 0, optimality=st["grad_norm_inf"],
-                                message="device Levenberg-Marquardt", lm=st)
+        want_jac = bool(jac) if jac != "auto" else 8 * int(gpu.problem.nnz) <= JAC_AUTO_LIMIT_BYTES
+        result = OptimizeResult(x=x, fun=fun, jac=jac_fn(x) if want_jac else None, cost=0.5 * float(fun @ fun),
+                                nfev=st["n_eval_normal"] + st["n_eval_cost"], njev=st["n_eval_normal"], status=st["status"],
+                                success=st["status"] > 0, optimality=st["grad_norm_inf"], message="device Levenberg-Marquardt", lm=st)
+        if not want_jac:
+            ne = gpu.problem.normal_equations(x, with_W=False)
+            result["normal_blocks"] = {k: ne[k] for k in ("U", "gc", "V", "gp", "cost")}
     else:
         raise ValueError("solver must be 'lm' or 'scipy'")
     end = time.time()

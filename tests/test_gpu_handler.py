@@ -136,3 +136,29 @@ def test_run_bundle_adjustment_reference_solver_path():
     res, camset = run_bundle_adjustment(h, solver="scipy")
     assert camset is None and res.nfev <= 8
     assert res.cost < 0.5 * float(g["r"] @ g["r"])
+
+
+def test_run_bundle_adjustment_without_the_explicit_jacobian():
+    """jac=False (what jac="auto" does above 2 GiB of CSR values): same solution, `jac` is None and
+    the block diagonal of J^T J at the solution travels instead; it equals the blocks of the explicit Jacobian."""
+    from pycamset_b200.handler import run_bundle_adjustment
+    g = load_case("ring4_template")
+    h = make_handler(g)
+    h.problem_opts["max_nfev"] = 20
+    res_a, _ = run_bundle_adjustment(h, solver="lm", jac=True)
+    h2 = make_handler(g)
+    h2.problem_opts["max_nfev"] = 20
+    res_b, _ = run_bundle_adjustment(h2, solver="lm", jac=False)
+    assert res_b.jac is None and res_b["jac"] is None
+    # two solves of the same problem: equal up to the order of the FP64 reductions inside the kernels
+    assert np.allclose(res_a.x, res_b.x, rtol=1e-7, atol=1e-10) and abs(res_a.cost - res_b.cost) <= 1e-9 * res_a.cost
+    nb = res_b["normal_blocks"]
+    C = int(g["n_cams"])
+    assert nb["U"].shape == (C, 15, 15) and nb["V"].shape[1:] == (6, 6)
+    assert abs(0.5 * nb["cost"] - res_b.cost) <= 1e-12 * res_b.cost      # r.r at the solution
+    # free-column Gram of the explicit Jacobian against the diagonal of the blocks (column order: free intr | extr | pose)
+    JtJ_diag = np.asarray(res_a.jac.multiply(res_a.jac).sum(axis=0)).ravel()
+    unfixed = np.asarray(g["unfixed"], bool)
+    full_diag = np.concatenate([np.stack([np.diag(U)[:9] for U in nb["U"]]).ravel(), np.stack([np.diag(U)[9:] for U in nb["U"]]).ravel(),
+                                np.stack([np.diag(V) for V in nb["V"]]).ravel()])
+    assert np.allclose(full_diag[unfixed], JtJ_diag, rtol=1e-9, atol=1e-12)
