@@ -1,5 +1,5 @@
 """A/B of the residual kernel variants on config 4 (device-resident): per-call time with the L2 flushed, and equality of
-the outputs.  Usage: PCS_RES_ROWS=0|1 [PCS_RES_CTAS=6] python tools/kres_ab.py [out.npy]"""
+the outputs.  Usage: [KRES_RIG=C,M,layout,detect_prob] python tools/kres_ab.py [out.npy]"""
 import sys, os, json
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,7 +30,7 @@ with torch.cuda.stream(stream):
         e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
 ms = float(np.median(ts))
-print(json.dumps({"variant": {k: os.environ.get(k) for k in ("PCS_RES_ROWS", "PCS_RES_CTAS")}, "rig": spec, "n_obs": N, "ms_per_call": ms,
+print(json.dumps({"rig": spec, "n_obs": N, "ms_per_call": ms,
                   "GBps_40B": 40.0 * N / ms / 1e6, "frac_hbm_40B": 40.0 * N / ms / 1e6 / 6544.7, "r_checksum": float(r.double().abs().sum())}))
 if len(sys.argv) > 1:
     np.save(sys.argv[1], r.cpu().numpy())
