@@ -763,10 +763,13 @@ def main():
         n_local, kern_avg_ms = main_res["n_obs_per_gpu"], main_res["kernel_ms"]
         achieved = ALGO_BYTES_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e9
         traffic = None
+        ncu_pipes = None   # measured pipe utilisation of the same kernel under ncu (next to the op-count estimate below)
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
             try:
-                traffic = json.loads(tf.read_text()).get(args.workload)
+                tj = json.loads(tf.read_text())
+                traffic = tj.get(args.workload)
+                ncu_pipes = tj.get(args.workload + "_ncu_pipes")
             except Exception:
                 traffic = None
         cpu = None
@@ -796,7 +799,7 @@ def main():
                          "note": "K_ne is bound by the FP64 pipe, not HBM (DESIGN.md 4); see the fp64 object",
                          "fp64": {"issued_tflops": FP64_ISSUED_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12,
                                   "useful_tflops": FP64_USEFUL_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12,
-                                  "peak_tflops": FP64_PEAK_TFLOPS, "peak_source": "measured (tools/fp64_peak.cu)",
+                                  "peak_tflops": FP64_PEAK_TFLOPS, "peak_source": "measured (tools/fp64_peak.cu)", "ncu": ncu_pipes,
                                   "frac_issued": FP64_ISSUED_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}},
             "cpu_baseline": cpu,
             "e2e": main_res["e2e"],
