@@ -796,7 +796,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "normal-equation kernel (K_ne)",
                          "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_obs": ALGO_BYTES_PER_OBS,
-                         "note": "K_ne is bound by the FP64 pipe, not HBM (DESIGN.md 4); see the fp64 object",
+                         "note": "K_ne is bound by the dispatch cycles of its FP64 / tensor-FP64 instructions, not by HBM (DESIGN.md 4, "
+                                 "profiles/r2_kne_knockout.txt); see the fp64 object",
                          "fp64": {"issued_tflops": FP64_ISSUED_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12,
                                   "useful_tflops": FP64_USEFUL_FLOP_PER_OBS * n_local / (kern_avg_ms * 1e-3) / 1e12,
                                   "peak_tflops": FP64_PEAK_TFLOPS, "peak_source": "measured (tools/fp64_peak.cu)", "ncu": ncu_pipes,
