@@ -3,7 +3,8 @@
 Sizes cover one tile, ragged last tiles and odd leading dimensions (n = 15 C is rarely a multiple of 32), the bench
 size (480 = 32 cameras), grids narrower than a phase's tile count (660 -> 252 tiles on 148 SMs), and systems whose row
 blocks no longer fit the shared-memory buffer of the back substitution and stream through it in chunks (n = 700 ... 2100:
-1503 = the reduced system of the ccube self-calibration, 1920 = 128 cameras).  Tolerance: relative solution error
+1503 = the reduced system of the ccube self-calibration with the poses eliminated, 1920 = 128 cameras; 4800 = more block columns
+than CTAs).  Tolerance: relative solution error
 <= 1e-9 * cond-scaled bound (the systems are built with cond ~ 1e4), residual <= 1e-11 relative."""
 import ctypes as ct
 
@@ -62,3 +63,18 @@ def test_spd_solve_large_identity_and_odd_leading_dimension():
     rc, info, x = _solve(n, A, b)
     assert rc == 0 and info == 0
     assert np.linalg.norm(A @ x - b) <= 1e-11 * (np.linalg.norm(A, 2) * np.linalg.norm(x) + np.linalg.norm(b))
+
+
+def test_spd_solve_more_block_columns_than_ctas():
+    """n = 4800: 150 block columns on a grid of at most 148 CTAs -- the panel is wider than the grid (single-tile visits in
+    the factorisation) and CTAs own more than one block column in the dataflow back substitution (a CTA walks its blocks
+    in descending order; the highest unfinished block can always proceed)."""
+    n = 4800
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((n, 64)) * 0.05
+    A = B @ B.T + np.diag(np.linspace(1.0, 3.0, n))      # SPD, well conditioned, dense
+    b = rng.standard_normal(n)
+    rc, info, x = _solve(n, A, b)
+    assert rc == 0 and info == 0
+    ref = np.linalg.solve(A, b)
+    assert np.linalg.norm(x - ref) <= 1e-10 * np.linalg.norm(ref)
