@@ -176,6 +176,9 @@ def test_two_ranks_self_calibration_chain():
                 unf = pdist.shard_param_string(unfixed, Cn, Mn, ranges[r], n_keys=Kn).astype(bool)
                 with BundleProblem(1, c_s, p_s, k_s, uv_s, Cn, ranges[r][1] - ranges[r][0], Kn, unfixed=unf) as p:
                     p.set_param_string(par)
+                    # builds the solver workspace while the problem is still single-rank (it then plans to eliminate the
+                    # points); the hook installed afterwards must make the solve rebuild it for the pose elimination
+                    assert p.lm_schur_fraction() == 1.0
                     p.set_allreduce(hs.hook(r), r, 2)
                     _, st = p.lm_solve(par[unf], max_iter=iters, ftol=0.0, xtol=0.0, gtol=0.0)
                     out[r] = (p.get_param_string(), st)
