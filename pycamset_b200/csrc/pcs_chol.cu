@@ -11,9 +11,13 @@
 //     diagonal tile itself -- A_kk minus the (lagged) rank-32 update with panel k-1 -- and factors it in one warp
 //     (row per lane, pivots broadcast by shuffles), so nobody waits for a "diagonal done" message; it then applies the
 //     lagged update to its own tile and solves it against L_kk^T.  Tiles right of the panel only get the lagged update.
-//   * After the last phase CTA 0 runs the back substitution  x = L^-T y  out of shared memory; a row block of L that does
-//     not fit the buffer (n > ~600) streams through it in chunks, so n is bounded by the device memory, not by the SM.
-// Tiles are assigned round-robin per phase, panel tiles first (one per CTA while the grid is wide enough).
+//   * The tiles right of the panel are visited in 2 x 2 groups that share their four operand tiles of panel k-1 and have
+//     all (up to) eight tile fetches in flight together: a visit is bound by the latency of its fetches from L2.
+//   * The back substitution  x = L^-T y  is a dataflow over the whole grid without barriers: block column k belongs to CTA
+//     (nb - 1 - k) mod grid, which streams the tiles of its column through a ring of shared-memory buffers, subtracts
+//     L_ik^T x_i as the x_i arrive in a sentinel-initialised mailbox (the data is the signal: no fence, no flag), solves
+//     its triangle in one warp and publishes x_k.  n is bounded by the device memory, not by the SM.
+// Work is assigned round-robin per phase, panel tiles first (one per CTA while the grid is wide enough), then the groups.
 // The kernel is launched cooperatively (co-residency is required by the barrier); loads of data written by other
 // CTAs bypass L1 (ld.global.cg).
 #include <algorithm>

@@ -9,10 +9,15 @@
 //                    dense SPD solve (k_chol_solve, pcs_chol.cu; cuSOLVER for systems too large for it),
 //                    back-substitute the poses, move to the trial point and evaluate it with the full
 //                    normal-equation kernel into the second output set -- one host synchronisation per iteration;
-//   self-calibration: the same step with the target points joining the cameras in the reduced system (15 C + 3 K
-//                    unknowns: point blocks Pk, camera x point blocks Xck on the A side, pose x point blocks Ymk next to W on
-//                    the coupling side); problems whose dense (camera, key) / (pose, key) tables would not fit fall back to the
-//                    dense (n_free x n_free) normal matrix + cuSOLVER Cholesky with a residual-only trial pass.
+//   self-calibration: poses AND target points are block diagonal but coupled to each other, so one of the two sets is
+//                    eliminated -- the larger one.  Points eliminated (3 K > 6 M, single rank): 3 x 3 Cholesky per point,
+//                    reduced system over cameras + poses [[U, .], [W^T, V]] - Z Z^T with Z = [Xck; Ymk] L_k^-T
+//                    (solve_points_eliminated).  Poses eliminated (otherwise): the points join the cameras in the reduced
+//                    system (15 C + 3 K unknowns: point blocks Pk, camera x point blocks Xck on the A side, pose x point
+//                    blocks Ymk next to W on the coupling side).  Problems whose dense (camera, key) / (pose, key) tables
+//                    would not fit fall back to the dense (n_free x n_free) normal matrix + cuSOLVER Cholesky with a
+//                    residual-only trial pass.
+//   The pose elimination skips the structurally zero blocks of Z (static unit list, pcs_schur.cu).
 // Marquardt scaling (lambda * diag(J^T J)) plays the role of x_scale='jac'; Nielsen's gain-ratio update
 // drives lambda.  Fixed parameters are rows / columns replaced by the identity.
 #include <cublas_v2.h>
