@@ -2,10 +2,15 @@
 //
 // The per-evaluation exchange of the pose-sharded problem is C * 240 + 1 doubles (61 KB at C = 32):
 // a latency problem, not a bandwidth one.  Every rank owns a "symmetric" buffer that all peers have mapped (the
-// Python host allocates it with torch's symmetric-memory allocator and passes the peer pointers in).  One CTA per
-// rank: write the local block into every peer's buffer (posted NVLink stores), raise a flag at every peer, wait for
-// every peer's flag, then add up the received blocks from local memory in rank order (bitwise identical result on
-// every rank).  Two data slots alternate so that a rank that races ahead never overwrites a block still being read.
+// Python host allocates it with torch's symmetric-memory allocator and passes the peer pointers in): flags, then two
+// slot sets of `world` blocks each, used alternately so that a rank that races ahead never overwrites a block still
+// being read.  Three kernels implement the exchange:
+//   * k_p2p_allreduce_sentinel (default) -- "the data is the signal": empty slots hold a sentinel NaN, a rank's block is
+//     pushed into its slot at every peer with plain posted stores, and the summing threads poll their own buffer's slots
+//     until the values they need have arrived; no system fence, no flag (7.6 us per exchange at N = 2);
+//   * k_p2p_allreduce / k_p2p_allreduce_multi (PCS_P2P_SENTINEL=0) -- the fence + flag protocol of round 1, single CTA or
+//     one CTA per peer: push, system fence, raise a flag at every peer, wait for every peer's flag, sum (10.4 us).
+// All of them sum the received blocks from LOCAL memory in rank order: the result is bitwise identical on every rank.
 #include <cstdlib>
 
 #include "pcs_internal.cuh"
